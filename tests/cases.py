@@ -1,0 +1,57 @@
+"""Builds oracle Data/State objects and injected draws for the parity cases shared by the CPU
+(oracle vs reference) and GPU (engine vs oracle) tests."""
+import numpy as np
+
+from oracle import oracle as orc
+from tests import synth
+
+CASES = {
+    # name: (kind, kwargs)   sizes are small enough for the CPU oracle to finish in seconds
+    "F_common": ("common", dict(seed=11, n=37, T=60, K=3, P=8, M=3)),
+    "F_common_K2M2": ("common", dict(seed=12, n=25, T=50, K=2, P=7, M=2)),
+    "F_ragged": ("ragged", dict(seed=13, n=31, K=3, P=8, M=2)),
+    "MV": ("mv", dict(seed=14, n=41, R=10, K=3, M=2)),
+    "F_cov": ("common", dict(seed=15, n=29, T=40, K=3, P=8, M=2, D=2)),
+    "F_cov_ragged": ("ragged", dict(seed=16, n=23, K=2, P=8, M=2, D=2)),
+    "MV_cov": ("mv", dict(seed=17, n=33, R=9, K=3, M=2, D=2)),
+}
+
+
+def build(name):
+    kind, kw = CASES[name]
+    if kind == "common":
+        s = synth.functional_common(**kw)
+        n, T = s["n"], s["T"]
+        off = np.arange(n + 1, dtype=np.int64) * T
+        d = orc.Data(n=n, K=s["K"], P=s["P"], M=s["M"], y=s["y"].ravel(), B=np.tile(s["B"], (n, 1)), off=off, X=s["X"])
+    elif kind == "ragged":
+        s = synth.functional_ragged(**kw)
+        d = orc.Data(n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], B=s["B"], off=s["off"], X=s["X"])
+    else:
+        s = synth.multivariate(**kw)
+        d = orc.Data(n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], X=s["X"], identity_basis=True)
+    par = s["par"]
+    st = orc.State(nu=par["nu"], Phi=par["Phi"], Z=s["Z"], chi=s["chi"], sigma_sq=par["sigma_sq"],
+                   eta=par["eta"], xi=par["xi"])
+    return s, d, st
+
+
+A_Z_PM = 20000.0
+
+
+def draws(name, s, a_Z_PM=A_Z_PM):
+    """Injected random draws for every update, seeded per case."""
+    rng = np.random.default_rng(sum(ord(c) for c in name) + 1000)
+    n, K, P, M, D = s["n"], s["K"], s["P"], s["M"], s.get("D", 0)
+    return dict(
+        gam=np.asfortranarray(rng.gamma(a_Z_PM * s["Z"])), u=rng.uniform(size=n),
+        eps=np.asfortranarray(rng.normal(size=(n, M))), gsig=rng.gamma(50.0),
+        z_nu=np.asfortranarray(rng.normal(size=(P, K))), z_phi=np.asfortranarray(rng.normal(size=(P, K * M))),
+        z_eta=np.asfortranarray(rng.normal(size=(P, max(D, 1) * K))),
+        z_xi=np.asfortranarray(rng.normal(size=(P, K * M * max(D, 1)))),
+        tau=rng.gamma(2.0, 1.0, K) + 0.1, gamma=np.asfortranarray(rng.gamma(2.0, 1.0, (K, P, M)) + 0.1),
+        tilde_tau=np.asfortranarray(rng.gamma(2.0, 1.0, (K, M)) + 0.5),
+        tau_eta=np.asfortranarray(rng.gamma(2.0, 1.0, (K, max(D, 1))) + 0.1),
+        gamma_xi=rng.gamma(2.0, 1.0, (K, P, max(D, 1), M)) + 0.1,
+        tilde_tau_xi=np.asfortranarray(rng.gamma(2.0, 1.0, (K, M, max(D, 1))) + 0.5),
+    )
