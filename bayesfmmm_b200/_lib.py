@@ -1,0 +1,64 @@
+"""Loader of libbfmmm_b200.so (ctypes).  Fails loudly when the CUDA extension is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libbfmmm_b200.so")
+_lib = None
+
+dp = C.POINTER(C.c_double)
+
+
+class Config(C.Structure):
+    _fields_ = [("model", C.c_int32), ("n", C.c_int32), ("K", C.c_int32), ("P", C.c_int32), ("M", C.c_int32),
+                ("D", C.c_int32), ("device", C.c_int32), ("common_grid", C.c_int32), ("T", C.c_int64),
+                ("off", C.POINTER(C.c_int64)), ("y", dp), ("B", dp), ("t", dp), ("degree", C.c_int32),
+                ("n_internal", C.c_int32), ("internal_knots", dp), ("boundary", C.c_double * 2), ("X", dp),
+                ("global_offset", C.c_int64)]
+
+
+# every symbol include/bfmmm.h and include/bfmmm_debug.h declare
+EXPORTS = [
+    "bfmmm_create", "bfmmm_destroy", "bfmmm_last_error", "bfmmm_launch_count", "bfmmm_get_basis",
+    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
+    "bfmmm_ssr", "bfmmm_suffstats", "bfmmm_get_gram", "bfmmm_seed", "bfmmm_stats_buffer_dev",
+    "bfmmm_update_z_async", "bfmmm_update_chi_async", "bfmmm_ssr_async", "bfmmm_suffstats_async",
+    "bfmmm_read_stats", "bfmmm_sync", "bfmmm_stream",
+    "bfmmm_debug_enable_acc", "bfmmm_debug_get_acc", "bfmmm_debug_update_z_rng", "bfmmm_debug_update_chi_rng",
+    "bfmmm_debug_get_cache",
+]
+
+
+def library_path() -> str:
+    return _LIB
+
+
+def build_library(jobs: int = 8, extra: str = "") -> str:
+    """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), f"-j{jobs}", "-s"]
+    if extra:
+        cmd.append(f"EXTRA={extra}")
+    subprocess.check_call(cmd)
+    return _LIB
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise RuntimeError(
+            f"{_LIB} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the sampler hot path)")
+    lib = C.CDLL(_LIB)
+    lib.bfmmm_last_error.restype = C.c_char_p
+    lib.bfmmm_launch_count.restype = C.c_int64
+    lib.bfmmm_stream.restype = C.c_void_p
+    lib.bfmmm_stream.argtypes = [C.c_void_p]
+    lib.bfmmm_destroy.restype = None
+    lib.bfmmm_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib

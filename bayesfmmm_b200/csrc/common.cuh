@@ -1,0 +1,207 @@
+// common.cuh -- shared definitions of the sm_100a kernels behind include/bfmmm.h.
+//
+// Data layout in HBM:
+//   Ct   [P][ld]  whitened projected coefficients  c~_i = L^{-1} B' y_i   (SoA: coefficient-major,
+//                 function index contiguous, ld = n rounded up to 8) -- the per-iteration kernels
+//                 stream this cache instead of the raw observations.
+//   rss  [ld]     ||y_i - B c_i||^2, the part of the residual orthogonal to the basis
+//   Z    [K][ld], chi [M][ld], X [D][ld]   (the reference's column-major n x K etc. with padded ld)
+//   glob [P][QS]  whitened global coefficients, feature-minor:
+//                 f = ((k*(M+1) + m')*(1+D) + d'), m'=0 mean block / m'=m+1 eigen block m,
+//                 d'=0 plain / d'=d+1 covariate d; QS = q rounded up to 2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bf {
+
+constexpr int VEC = 2;          // functions per thread in the per-function passes (16-byte loads)
+constexpr int DMAX = 4;         // covariates supported by the covariate-adjusted kernels
+constexpr int PF_THREADS = 128; // block size of the per-function passes
+constexpr int RED_MAX = 8;      // values reduced per block in the per-function passes (K+1 <= 8)
+
+struct PassArgs {
+  int n, ld, P, D, QS;
+  const double* __restrict__ Ct;
+  const double* __restrict__ rss;
+  double* __restrict__ Z;
+  double* __restrict__ chi;
+  const double* __restrict__ X;
+  const double* __restrict__ glob;
+  double sigma_sq, beta;
+  // Z step
+  double alpha3, a_Z_PM;
+  double pi[8];
+  const double* __restrict__ gam;   // injected draws [K][ld] or nullptr (device RNG)
+  const double* __restrict__ u;     // [ld] or nullptr
+  const double* __restrict__ eps;   // chi: [M][ld] or nullptr
+  double* __restrict__ acc_out;     // optional per-function acceptance log-ratio (diagnostics)
+  double* __restrict__ draws_out;   // optional: device-RNG draws written back ([K+1][ld] / [M][ld])
+  // RNG
+  uint64_t key, iteration, global_offset;
+  // reduction
+  double* __restrict__ partials;    // [gridDim.x][RED_MAX]
+  unsigned int* __restrict__ ticket;
+  double* __restrict__ out;         // final reduced values (stats buffer slots)
+  int n_out;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter-based)
+struct Philox {
+  uint32_t k0, k1;
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ static inline void block(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, c[0], hi0, lo0);
+      mulhilo(0xCD9E8D57u, c[2], hi1, lo1);
+      uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+      c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+  }
+};
+
+// Stream of doubles for one (function, iteration, purpose): counter = (index lo, index hi,
+// iteration*64 + purpose, running block number).  Results depend only on the GLOBAL function
+// index, so a chain is independent of how functions are sharded over GPUs.
+struct RngStream {
+  uint32_t c0, c1, c2, ctr, k0, k1;
+  double spare; int have;
+  __host__ __device__ RngStream(uint64_t key, uint64_t index, uint64_t iteration, uint32_t purpose)
+      : c0((uint32_t)index), c1((uint32_t)(index >> 32)), c2((uint32_t)(iteration * 64 + purpose)), ctr(0),
+        k0((uint32_t)key), k1((uint32_t)(key >> 32)), spare(0), have(0) {}
+  __host__ __device__ inline double uniform() {     // (0,1), 53 bits
+    if (have) { have = 0; return spare; }
+    uint32_t c[4] = {c0, c1, c2, ctr++};
+    Philox::block(c, k0, k1);
+    uint64_t a = ((uint64_t)c[0] << 32) | c[1], b = ((uint64_t)c[2] << 32) | c[3];
+    spare = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    have = 1;
+    return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  __host__ __device__ inline double normal() {      // Box-Muller, one value per two uniforms
+    double u1 = uniform(), u2 = uniform();
+    double r = sqrt(-2.0 * log(u1));
+#ifdef __CUDA_ARCH__
+    return r * cospi(2.0 * u2);
+#else
+    return r * cos(6.283185307179586476925286766559 * u2);
+#endif
+  }
+  // Marsaglia-Tsang; shape < 1 boosted by U^(1/shape)
+  __host__ __device__ inline double gamma(double shape) {
+    double boost = 1.0;
+    if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+    double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 64; it++) {
+      double x = normal();
+      double v = 1.0 + c * x;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      double uu = uniform();
+      double x2 = x * x;
+      if (uu < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
+      if (log(uu) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+    return boost * d;   // unreachable in practice (acceptance > 95% per trial)
+  }
+};
+enum { RNG_Z_PROPOSAL = 1, RNG_Z_ACCEPT = 2, RNG_CHI = 3 };
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ld2_stream(const double* p) {      // streamed once: bypass L1
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic grid reduction of NV per-thread values: warp shuffle -> shared -> one partial row per
+// block -> the last block to finish (ticket) sums the rows in a fixed order and writes `out`.
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) {
+  __shared__ double s_part[PF_THREADS / 32][RED_MAX];
+  __shared__ unsigned int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    double w = warp_sum(v[j]);
+    if (lane == 0) s_part[warp][j] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_part[w][threadIdx.x];
+    a.partials[(size_t)blockIdx.x * RED_MAX + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block: NV values, each summed over gridDim.x rows by the whole block in a fixed pattern
+  for (int j = 0; j < NV; j++) {
+    double t = 0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      t += __ldcg(&a.partials[(size_t)b * RED_MAX + j]);
+    t = warp_sum(t);
+    __syncthreads();
+    if (lane == 0) s_part[warp][0] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_part[w][0];
+      a.out[j] = tot;
+    }
+  }
+  if (threadIdx.x == 0) *a.ticket = 0u;
+}
+
+// launchers implemented in the per-kernel translation units
+int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
+int pass_grid(int n);
+
+struct StatsArgs {
+  int n, ld, P, K, M, D, q;
+  const double* __restrict__ Ct;
+  const double* __restrict__ Z;
+  const double* __restrict__ chi;
+  const double* __restrict__ X;
+  double* __restrict__ partials;   // [blocks][rows]
+  double* __restrict__ WtW;        // q x q column-major (device)
+  double* __restrict__ CtW;        // P x q column-major (device, whitened)
+  int blocks;
+};
+int launch_stats(const StatsArgs& a, cudaStream_t s);
+int stats_blocks(int sm_count);
+size_t stats_partial_doubles(int P, int q, int blocks);
+
+struct ProjectArgs {
+  int n, ld, P; int64_t T; int64_t i_begin;   // functions [i_begin, i_begin + n) of the shard
+  const double* __restrict__ Y;      // n x T row-major (this chunk)
+  const double* __restrict__ Q;      // T x P row-major orthonormal basis Q = B L^{-T}
+  double* __restrict__ Ct;           // [P][ld]
+  double* __restrict__ rss;          // [ld]
+};
+int launch_project(const ProjectArgs& a, cudaStream_t s);
+int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots, int degree, int P,
+                   double* B_rowmajor, cudaStream_t s);
+
+extern unsigned long long g_launch_count;
+}  // namespace bf

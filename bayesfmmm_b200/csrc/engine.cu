@@ -1,0 +1,548 @@
+// engine.cu -- the C ABI of include/bfmmm.h: device memory, create-time projection, launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bfmmm.h"
+#include "common.cuh"
+
+namespace bf { unsigned long long g_launch_count = 0; }
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+#define CU(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t _e = (x);                                                              \
+    if (_e != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int N_STAGE = 4;
+}  // namespace
+
+struct bfmmm_engine {
+  int model = 0, n = 0, ld = 0, K = 0, P = 0, M = 0, D = 0, q = 0, QS = 0, device = 0;
+  int64_t T = 0;
+  bool common = true, identity = false;
+  int64_t global_offset = 0;
+  double n_points = 0, sum_half = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  // device
+  double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
+  double *draws = nullptr, *stats = nullptr, *partials = nullptr, *st_partials = nullptr, *acc_dbg = nullptr;
+  unsigned int* ticket = nullptr;
+  int64_t stats_len = 0;
+  int pass_blocks = 0, st_blocks = 0;
+  // host
+  std::vector<double> B, G, L;       // basis T x P row-major, Gram P x P col-major, chol lower col-major
+  double* h_stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
+  int stage_next = 0;
+  double* h_stats = nullptr;
+  double sigma_sq = 1.0;
+  uint64_t key = 0x9E3779B97F4A7C15ull, iteration = 0;
+  // offsets into stats
+  int off_slz() const { return 0; }
+  int off_acc() const { return K; }
+  int off_ssr() const { return K + 1; }
+  int off_ssr_after() const { return K + 2; }
+  int off_wtw() const { return K + 3; }
+  int off_ctw() const { return K + 3 + q * q; }
+};
+
+namespace {
+
+bool chol_lower(int n, const std::vector<double>& A, std::vector<double>& L) {
+  L.assign((size_t)n * n, 0.0);
+  for (int j = 0; j < n; j++) {
+    double s = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) s -= L[(size_t)k * n + j] * L[(size_t)k * n + j];
+    if (!(s > 0)) return false;
+    double d = std::sqrt(s);
+    L[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double t = A[(size_t)j * n + i];
+      for (int k = 0; k < j; k++) t -= L[(size_t)k * n + i] * L[(size_t)k * n + j];
+      L[(size_t)j * n + i] = t / d;
+    }
+  }
+  return true;
+}
+
+void free_all(bfmmm_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
+  cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
+  cudaFree(e->acc_dbg);
+  for (int i = 0; i < N_STAGE; i++) {
+    if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+    if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
+  }
+  if (e->h_stats) cudaFreeHost(e->h_stats);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+// host (n x cols, column-major, leading dimension n) -> device [cols][ld]
+int upload_cols(bfmmm_engine* e, double* dst, const double* src, int cols) {
+  if (cols == 0) return 0;
+  CU(cudaMemcpy2DAsync(dst, (size_t)e->ld * 8, src, (size_t)e->n * 8, (size_t)e->n * 8, cols, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+int download_cols(bfmmm_engine* e, double* dst, const double* src, int cols) {
+  if (cols == 0) return 0;
+  CU(cudaMemcpy2DAsync(dst, (size_t)e->n * 8, src, (size_t)e->ld * 8, (size_t)e->n * 8, cols, cudaMemcpyDeviceToHost, e->stream));
+  return 0;
+}
+
+int build_basis(bfmmm_engine* e, const bfmmm_config* c) {
+  const int P = e->P;
+  const int64_t T = e->T;
+  e->B.assign((size_t)T * P, 0.0);
+  if (c->B) {
+    std::copy(c->B, c->B + (size_t)T * P, e->B.begin());
+  } else {
+    if (!c->t || (c->n_internal > 0 && !c->internal_knots)) return fail("bfmmm_create: neither B nor a spline description (t, knots) was given");
+    if (c->n_internal + c->degree + 1 != P) return fail("bfmmm_create: P != n_internal + degree + 1");
+    int nk = c->n_internal + 2 * (c->degree + 1);
+    std::vector<double> kn(nk);
+    for (int i = 0; i <= c->degree; i++) { kn[i] = c->boundary[0]; kn[nk - 1 - i] = c->boundary[1]; }
+    for (int i = 0; i < c->n_internal; i++) kn[c->degree + 1 + i] = c->internal_knots[i];
+    double *d_t = nullptr, *d_kn = nullptr, *d_B = nullptr;
+    CU(cudaMalloc(&d_t, T * 8)); CU(cudaMalloc(&d_kn, nk * 8)); CU(cudaMalloc(&d_B, (size_t)T * P * 8));
+    CU(cudaMemcpyAsync(d_t, c->t, T * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_kn, kn.data(), nk * 8, cudaMemcpyHostToDevice, e->stream));
+    if (bf::launch_bspline(d_t, T, d_kn, nk, c->degree, P, d_B, e->stream)) return fail("bspline kernel launch failed");
+    CU(cudaMemcpyAsync(e->B.data(), d_B, (size_t)T * P * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_t); cudaFree(d_kn); cudaFree(d_B);
+  }
+  // Gram and its Cholesky factor
+  e->G.assign((size_t)P * P, 0.0);
+  for (int64_t t = 0; t < T; t++) {
+    const double* b = &e->B[(size_t)t * P];
+    for (int cc = 0; cc < P; cc++) {
+      if (b[cc] == 0.0) continue;
+      for (int r = 0; r < P; r++) e->G[(size_t)cc * P + r] += b[cc] * b[r];
+    }
+  }
+  if (!chol_lower(P, e->G, e->L))
+    return fail("bfmmm_create: B'B is not positive definite (a basis function has no support on the grid)");
+  return 0;
+}
+
+int project_common(bfmmm_engine* e, const bfmmm_config* c) {
+  const int P = e->P;
+  const int64_t T = e->T;
+  // Q = B L^{-T}: row t of Q solves L q = b_t
+  std::vector<double> Q((size_t)T * P);
+  for (int64_t t = 0; t < T; t++) {
+    const double* b = &e->B[(size_t)t * P];
+    double* qv = &Q[(size_t)t * P];
+    for (int i = 0; i < P; i++) {
+      double s = b[i];
+      for (int k = 0; k < i; k++) s -= e->L[(size_t)k * P + i] * qv[k];
+      qv[i] = s / e->L[(size_t)i * P + i];
+    }
+  }
+  double* d_Q = nullptr;
+  CU(cudaMalloc(&d_Q, (size_t)T * P * 8));
+  CU(cudaMemcpyAsync(d_Q, Q.data(), (size_t)T * P * 8, cudaMemcpyHostToDevice, e->stream));
+  // stream the observations through a bounded device buffer
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->n, (int64_t)(1ull << 30) / (T * 8)));
+  double* d_Y = nullptr;
+  CU(cudaMalloc(&d_Y, (size_t)chunk * T * 8));
+  for (int64_t i0 = 0; i0 < e->n; i0 += chunk) {
+    int64_t m = std::min<int64_t>(chunk, e->n - i0);
+    CU(cudaMemcpyAsync(d_Y, c->y + i0 * T, (size_t)m * T * 8, cudaMemcpyHostToDevice, e->stream));
+    bf::ProjectArgs pa;
+    pa.n = (int)m; pa.ld = e->ld; pa.P = P; pa.T = T; pa.i_begin = i0; pa.Y = d_Y; pa.Q = d_Q; pa.Ct = e->Ct; pa.rss = e->rss;
+    if (bf::launch_project(pa, e->stream)) return fail("project kernel launch failed");
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  cudaFree(d_Y); cudaFree(d_Q);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bfmmm_last_error(void) { return g_err.c_str(); }
+int64_t bfmmm_launch_count(void) { return (int64_t)bf::g_launch_count; }
+
+int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
+  if (!c || !out) return fail("bfmmm_create: null argument");
+  *out = nullptr;
+  if (c->n <= 0 || c->K < 2 || c->K > 6 || c->M < 1 || c->M > 6 || c->P < 1)
+    return fail("bfmmm_create: unsupported shape (need n > 0, 2 <= K <= 6, 1 <= M <= 6, P >= 1)");
+  if (c->D < 0 || c->D > bf::DMAX) return fail("bfmmm_create: D must be in [0, 4]");
+  if (c->D > 0 && !c->X) return fail("bfmmm_create: D > 0 but X is NULL");
+  if (!c->y) return fail("bfmmm_create: y is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("bfmmm_create: no CUDA device (this engine has no CPU fallback)");
+  if (c->device < 0 || c->device >= ndev) return fail("bfmmm_create: bad device ordinal");
+  CU(cudaSetDevice(c->device));
+  bfmmm_engine* e = new bfmmm_engine();
+  e->model = c->model; e->n = c->n; e->K = c->K; e->P = c->P; e->M = c->M; e->D = c->D; e->device = c->device;
+  e->identity = (c->model == BFMMM_MULTIVARIATE);
+  e->common = e->identity || c->common_grid;
+  e->T = e->identity ? c->P : c->T;
+  e->global_offset = c->global_offset;
+  e->ld = (c->n + 7) & ~7;
+  e->q = c->K * (1 + c->D) * (1 + c->M);
+  e->QS = (e->q + 1) & ~1;
+  if (!e->common) { delete e; return fail("bfmmm_create: ragged grids are not supported by this build yet"); }
+  if (!e->identity && e->T < 1) { delete e; return fail("bfmmm_create: common grid needs T >= 1"); }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, c->device);
+  e->sm_count = prop.multiProcessorCount;
+  auto bail = [&](int) { free_all(e); return 1; };
+#define CUE(x)                                                                  \
+  do {                                                                          \
+    cudaError_t _e = (x);                                                       \
+    if (_e != cudaSuccess) { fail(std::string(#x) + ": " + cudaGetErrorString(_e)); return bail(1); } \
+  } while (0)
+  CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  const size_t ld = e->ld;
+  CUE(cudaMalloc(&e->Ct, ld * e->P * 8));
+  CUE(cudaMalloc(&e->rss, ld * 8));
+  CUE(cudaMalloc(&e->Z, ld * e->K * 8));
+  CUE(cudaMalloc(&e->chi, ld * e->M * 8));
+  if (e->D) CUE(cudaMalloc(&e->X, ld * e->D * 8));
+  CUE(cudaMalloc(&e->glob, (size_t)e->P * e->QS * 8));
+  CUE(cudaMalloc(&e->draws, ld * (std::max(e->K + 1, e->M)) * 8));
+  e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q;
+  CUE(cudaMalloc(&e->stats, e->stats_len * 8));
+  e->pass_blocks = bf::pass_grid(e->ld);
+  CUE(cudaMalloc(&e->partials, (size_t)e->pass_blocks * bf::RED_MAX * 8));
+  e->st_blocks = bf::stats_blocks(e->sm_count);
+  CUE(cudaMalloc(&e->st_partials, bf::stats_partial_doubles(e->P, e->q, e->st_blocks) * 8));
+  CUE(cudaMalloc(&e->ticket, 4));
+  CUE(cudaMemsetAsync(e->ticket, 0, 4, e->stream));
+  CUE(cudaMemsetAsync(e->Ct, 0, ld * e->P * 8, e->stream));
+  CUE(cudaMemsetAsync(e->rss, 0, ld * 8, e->stream));
+  CUE(cudaMemsetAsync(e->Z, 0, ld * e->K * 8, e->stream));
+  CUE(cudaMemsetAsync(e->chi, 0, ld * e->M * 8, e->stream));
+  CUE(cudaMemsetAsync(e->stats, 0, e->stats_len * 8, e->stream));
+  CUE(cudaMemsetAsync(e->draws, 0, ld * (std::max(e->K + 1, e->M)) * 8, e->stream));
+  if (e->D) CUE(cudaMemsetAsync(e->X, 0, ld * e->D * 8, e->stream));
+  for (int i = 0; i < N_STAGE; i++) {
+    CUE(cudaMallocHost(&e->h_stage[i], (size_t)e->P * e->QS * 8));
+    CUE(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
+  }
+  CUE(cudaMallocHost(&e->h_stats, e->stats_len * 8));
+  if (e->identity) {
+    e->G.assign((size_t)e->P * e->P, 0.0);
+    e->L.assign((size_t)e->P * e->P, 0.0);
+    for (int p = 0; p < e->P; p++) { e->G[(size_t)p * e->P + p] = 1; e->L[(size_t)p * e->P + p] = 1; }
+    if (upload_cols(e, e->Ct, c->y, e->P)) return bail(1);      // c~_i = y_i, rss_i = 0
+    e->n_points = (double)e->n * e->P;
+    e->sum_half = (double)(((int64_t)e->n * e->P) / 2);          // y_obs.n_elem / 2, UpdateSigma.h:150
+  } else {
+    if (build_basis(e, c)) return bail(1);
+    if (project_common(e, c)) return bail(1);
+    e->n_points = (double)e->n * (double)e->T;
+    e->sum_half = (double)e->n * (double)(e->T / 2);             // sum_i floor(n_i / 2), UpdateSigma.h:49
+  }
+  if (e->D && upload_cols(e, e->X, c->X, e->D)) return bail(1);
+  CUE(cudaStreamSynchronize(e->stream));
+#undef CUE
+  *out = e;
+  return 0;
+}
+
+void bfmmm_destroy(bfmmm_engine* e) { free_all(e); }
+
+int bfmmm_get_basis(bfmmm_engine* e, double* B_out) {
+  if (!e || e->identity) return fail("bfmmm_get_basis: no basis for this model");
+  std::copy(e->B.begin(), e->B.end(), B_out);
+  return 0;
+}
+int bfmmm_get_gram(bfmmm_engine* e, double* G) {
+  if (!e) return fail("null engine");
+  std::copy(e->G.begin(), e->G.end(), G);
+  return 0;
+}
+
+int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (Z && upload_cols(e, e->Z, Z, e->K)) return 1;
+  if (chi && upload_cols(e, e->chi, chi, e->M)) return 1;
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int bfmmm_get_state(bfmmm_engine* e, double* Z, double* chi) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (Z && download_cols(e, Z, e->Z, e->K)) return 1;
+  if (chi && download_cols(e, chi, e->chi, e->M)) return 1;
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// whitened coefficient of feature f: c~ = L' c
+int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, const double* eta,
+                      const double* xi, double sigma_sq) {
+  if (!e) return fail("null engine");
+  if (!nu || (e->M > 0 && !Phi) || (e->D > 0 && (!eta || !xi))) return fail("bfmmm_set_globals: null block");
+  if (!(sigma_sq > 0)) return fail("bfmmm_set_globals: sigma_sq must be positive");
+  CU(cudaSetDevice(e->device));
+  const int K = e->K, P = e->P, M = e->M, D = e->D, QS = e->QS;
+  int slot = e->stage_next;
+  e->stage_next = (slot + 1) % N_STAGE;
+  CU(cudaEventSynchronize(e->ev_stage[slot]));
+  double* h = e->h_stage[slot];
+  std::vector<double> cvec(P);
+  for (int f = 0; f < e->q; f++) {
+    int dd = f % (1 + D), km = f / (1 + D), mm = km % (M + 1), k = km / (M + 1);
+    for (int p = 0; p < P; p++) {
+      double v;
+      if (mm == 0 && dd == 0) v = nu[(size_t)p * K + k];
+      else if (mm == 0) v = eta[((size_t)k * D + (dd - 1)) * P + p];
+      else if (dd == 0) v = Phi[((size_t)(mm - 1) * P + p) * K + k];
+      else v = xi[(size_t)k * P * D * M + ((size_t)(mm - 1) * D + (dd - 1)) * P + p];
+      cvec[p] = v;
+    }
+    if (e->identity) {
+      for (int p = 0; p < P; p++) h[(size_t)p * QS + f] = cvec[p];
+    } else {
+      for (int p = 0; p < P; p++) {
+        double s = 0;
+        for (int r = p; r < P; r++) s += e->L[(size_t)p * P + r] * cvec[r];   // (L')[p][r] = L[r][p]
+        h[(size_t)p * QS + f] = s;
+      }
+    }
+  }
+  for (int p = 0; p < P; p++)
+    for (int f = e->q; f < QS; f++) h[(size_t)p * QS + f] = 0.0;
+  CU(cudaMemcpyAsync(e->glob, h, (size_t)P * QS * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaEventRecord(e->ev_stage[slot], e->stream));
+  e->sigma_sq = sigma_sq;
+  return 0;
+}
+
+static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
+  std::memset(&a, 0, sizeof(a));
+  a.n = e->n; a.ld = e->ld; a.P = e->P; a.D = e->D; a.QS = e->QS;
+  a.Ct = e->Ct; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
+  a.sigma_sq = e->sigma_sq; a.beta = beta;
+  a.key = e->key; a.iteration = e->iteration; a.global_offset = (uint64_t)e->global_offset;
+  a.partials = e->partials; a.ticket = e->ticket;
+}
+
+static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta, bool injected,
+                    bool dump_draws) {
+  bf::PassArgs a;
+  fill_pass(e, a, beta);
+  a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM;
+  for (int k = 0; k < e->K; k++) a.pi[k] = pi[k];
+  if (injected) { a.gam = e->draws; a.u = e->draws + (size_t)e->K * e->ld; }
+  if (dump_draws) a.draws_out = e->draws;
+  a.acc_out = e->acc_dbg;
+  a.out = e->stats + e->off_slz(); a.n_out = e->K + 1;
+  int rc = bf::launch_z(a, e->K, e->M, e->stream);
+  if (rc) return fail("z kernel launch failed rc=" + std::to_string(rc));
+  return 0;
+}
+
+int bfmmm_update_z_async(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta) {
+  if (!e || !pi) return fail("null argument");
+  CU(cudaSetDevice(e->device));
+  return z_launch(e, pi, alpha3, a_Z_PM, beta, false, false);
+}
+
+int bfmmm_update_z(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta,
+                   const double* gam, const double* u, double* sum_log_Z, int64_t* n_accept) {
+  if (!e || !pi) return fail("null argument");
+  if ((gam == nullptr) != (u == nullptr)) return fail("bfmmm_update_z: gam and u must both be given or both be NULL");
+  CU(cudaSetDevice(e->device));
+  if (gam) {
+    if (upload_cols(e, e->draws, gam, e->K)) return 1;
+    if (upload_cols(e, e->draws + (size_t)e->K * e->ld, u, 1)) return 1;
+  }
+  if (z_launch(e, pi, alpha3, a_Z_PM, beta, gam != nullptr, false)) return 1;
+  CU(cudaMemcpyAsync(e->h_stats, e->stats + e->off_slz(), (e->K + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (sum_log_Z) std::copy(e->h_stats, e->h_stats + e->K, sum_log_Z);
+  if (n_accept) *n_accept = (int64_t)std::llround(e->h_stats[e->K]);
+  return 0;
+}
+
+static int chi_launch(bfmmm_engine* e, double beta, bool injected) {
+  bf::PassArgs a;
+  fill_pass(e, a, beta);
+  if (injected) a.eps = e->draws;
+  a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
+  int rc = bf::launch_chi(a, e->K, e->M, e->stream);
+  if (rc) return fail("chi kernel launch failed rc=" + std::to_string(rc));
+  return 0;
+}
+int bfmmm_update_chi_async(bfmmm_engine* e, double beta) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  return chi_launch(e, beta, false);
+}
+int bfmmm_update_chi(bfmmm_engine* e, double beta, const double* eps, double* ssr_after) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (eps && upload_cols(e, e->draws, eps, e->M)) return 1;
+  if (chi_launch(e, beta, eps != nullptr)) return 1;
+  CU(cudaMemcpyAsync(e->h_stats, e->stats + e->off_ssr_after(), 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (ssr_after) *ssr_after = e->h_stats[0];
+  return 0;
+}
+
+int bfmmm_ssr_async(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  bf::PassArgs a;
+  fill_pass(e, a, 1.0);
+  a.out = e->stats + e->off_ssr(); a.n_out = 1;
+  int rc = bf::launch_ssr(a, e->K, e->M, e->stream);
+  if (rc) return fail("ssr kernel launch failed rc=" + std::to_string(rc));
+  return 0;
+}
+int bfmmm_ssr(bfmmm_engine* e, double* ssr, double* sum_half, double* n_points) {
+  if (bfmmm_ssr_async(e)) return 1;
+  CU(cudaMemcpyAsync(e->h_stats, e->stats + e->off_ssr(), 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (ssr) *ssr = e->h_stats[0];
+  if (sum_half) *sum_half = e->sum_half;
+  if (n_points) *n_points = e->n_points;
+  return 0;
+}
+
+int bfmmm_suffstats_async(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  bf::StatsArgs a;
+  a.n = e->n; a.ld = e->ld; a.P = e->P; a.K = e->K; a.M = e->M; a.D = e->D; a.q = e->q;
+  a.Ct = e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
+  a.WtW = e->stats + e->off_wtw(); a.CtW = e->stats + e->off_ctw(); a.blocks = e->st_blocks;
+  int rc = bf::launch_stats(a, e->stream);
+  if (rc) return fail("stats kernel launch failed rc=" + std::to_string(rc));
+  return 0;
+}
+
+// B'Y'W = L * (C~'W)
+static void unwhiten(const bfmmm_engine* e, const double* CtW, double* BtYW) {
+  const int P = e->P;
+  for (int f = 0; f < e->q; f++)
+    for (int r = 0; r < P; r++) {
+      if (e->identity) { BtYW[(size_t)f * P + r] = CtW[(size_t)f * P + r]; continue; }
+      double s = 0;
+      for (int k = 0; k <= r; k++) s += e->L[(size_t)k * P + r] * CtW[(size_t)f * P + k];
+      BtYW[(size_t)f * P + r] = s;
+    }
+}
+
+int bfmmm_suffstats(bfmmm_engine* e, double* WtW, double* BtYW) {
+  if (bfmmm_suffstats_async(e)) return 1;
+  const int64_t len = (int64_t)e->q * e->q + (int64_t)e->P * e->q;
+  CU(cudaMemcpyAsync(e->h_stats + e->off_wtw(), e->stats + e->off_wtw(), len * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (WtW) std::copy(e->h_stats + e->off_wtw(), e->h_stats + e->off_ctw(), WtW);
+  if (BtYW) unwhiten(e, e->h_stats + e->off_ctw(), BtYW);
+  return 0;
+}
+
+int bfmmm_seed(bfmmm_engine* e, uint64_t key, uint64_t iteration) {
+  if (!e) return fail("null engine");
+  e->key = key; e->iteration = iteration;
+  return 0;
+}
+
+int bfmmm_stats_buffer_dev(bfmmm_engine* e, double** ptr, int64_t* len) {
+  if (!e) return fail("null engine");
+  *ptr = e->stats; *len = e->stats_len;
+  return 0;
+}
+int bfmmm_read_stats(bfmmm_engine* e, double* out, int64_t len) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (len > e->stats_len) len = e->stats_len;
+  CU(cudaMemcpyAsync(e->h_stats, e->stats, len * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  // the C~'W block is returned un-whitened (B'Y'W), like bfmmm_suffstats
+  std::vector<double> tmp;
+  if (len >= e->stats_len) {
+    tmp.resize((size_t)e->P * e->q);
+    unwhiten(e, e->h_stats + e->off_ctw(), tmp.data());
+    std::copy(tmp.begin(), tmp.end(), e->h_stats + e->off_ctw());
+  }
+  std::copy(e->h_stats, e->h_stats + len, out);
+  return 0;
+}
+int bfmmm_sync(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+void* bfmmm_stream(bfmmm_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+// ---- diagnostics used by the parity tests (declared in bfmmm_debug.h) ----
+// per-function acceptance log-ratio of the last/next Z steps is written to an internal buffer
+int bfmmm_debug_enable_acc(bfmmm_engine* e, int on) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (on && !e->acc_dbg) CU(cudaMalloc(&e->acc_dbg, (size_t)e->ld * 8));
+  if (!on && e->acc_dbg) { cudaFree(e->acc_dbg); e->acc_dbg = nullptr; }
+  return 0;
+}
+int bfmmm_debug_get_acc(bfmmm_engine* e, double* acc) {
+  if (!e || !e->acc_dbg) return fail("acc diagnostics not enabled");
+  CU(cudaMemcpyAsync(acc, e->acc_dbg, (size_t)e->n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+// device-RNG Z step that also returns the draws it used (gam n x K, u n), so the oracle can be
+// run on exactly the same draws
+int bfmmm_debug_update_z_rng(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta,
+                             double* gam_out, double* u_out) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (z_launch(e, pi, alpha3, a_Z_PM, beta, false, true)) return 1;
+  if (download_cols(e, gam_out, e->draws, e->K)) return 1;
+  if (download_cols(e, u_out, e->draws + (size_t)e->K * e->ld, 1)) return 1;
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  bf::PassArgs a;
+  fill_pass(e, a, beta);
+  a.draws_out = e->draws;
+  a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
+  if (bf::launch_chi(a, e->K, e->M, e->stream)) return fail("chi kernel launch failed");
+  if (download_cols(e, eps_out, e->draws, e->M)) return 1;
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+// the projected cache itself: C~ (n x P column-major) and rss (n)
+int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (Ct && download_cols(e, Ct, e->Ct, e->P)) return 1;
+  if (rss && download_cols(e, rss, e->rss, 1)) return 1;
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+namespace bf {
+int pass_grid(int ld) { return (ld + PF_THREADS * VEC - 1) / (PF_THREADS * VEC); }
+}

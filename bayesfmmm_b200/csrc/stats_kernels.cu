@@ -1,0 +1,204 @@
+// stats_kernels.cu -- sufficient-statistic contraction on the FP64 tensor-core path (DMMA).
+//
+// Feeds updateNu / updatePhi / updateEta / updateXi (reference UpdateNu.h:42-63,
+// UpdatePhi.h:44-71, UpdateEta.h:51-81, UpdateXi.h:51-72).  Those loops accumulate, per block a,
+//   M_a = sum_i w_ia^2 B_i'B_i,   m_a = sum_i w_ia B_i'(y_i - B_i sum_{b != a} w_ib c_b)
+// with one full data pass per block.  On a common basis all of them are functions of
+//   W'W  (q x q)   and   C~'W  (P x q),     W[i][f] = feature weight, C~ = whitened coefficients,
+// which this kernel produces in ONE pass:  [C~ ; W]' W  is a GEMM whose K dimension is the
+// function index (split-K over the whole grid).
+//
+// Mapping onto mma.sync.m8n8k4.f64 (SASS DMMA): the function index is the MMA K dimension, and
+// because a sum over functions is order-free the four K slots of one MMA are fed with functions
+// {2c} (and the next MMA with {2c+1}) of an 8-function chunk, where c = lane%4.  Every thread
+// therefore issues only 16-byte loads, four lanes cover 64 contiguous bytes of a row, and no
+// shared-memory transpose is needed:
+//   A fragment (8x4)  a = C~[p = 8*mt + lane/4][function slot c]         (rows p >= P are zero)
+//   B fragment (4x8)  b = W [function slot c][feature f = 8*nt + lane/4] (computed on the fly
+//                         from Z, chi, X: w = Z_k * chi_m * x_d)
+//   W'W tiles reuse the same registers: A = W' fragment (row = feature, col = slot) == b.
+#include "common.cuh"
+
+namespace bf {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_WARPS = ST_THREADS / 32;
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
+  constexpr int TILES = MT * NT + NT * NT;
+  __shared__ double s_acc[TILES * 64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const int mt0 = blockIdx.y * MT;
+  const bool do_wtw = (blockIdx.y == 0);
+
+  // feature owned by this thread in each n-tile
+  const double* zp[NT];
+  const double* cp[NT];
+  const double* xp[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) {
+    int f = nt * 8 + g;
+    zp[nt] = nullptr; cp[nt] = nullptr; xp[nt] = nullptr;
+    if (f < a.q) {
+      int dd = f % (1 + a.D);
+      int km = f / (1 + a.D);
+      int mm = km % (a.M + 1), k = km / (a.M + 1);
+      zp[nt] = a.Z + (size_t)k * a.ld;
+      if (mm > 0) cp[nt] = a.chi + (size_t)(mm - 1) * a.ld;
+      if (dd > 0) xp[nt] = a.X + (size_t)(dd - 1) * a.ld;
+    }
+  }
+  const double* ap[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) {
+    int p = (mt0 + mt) * 8 + g;
+    ap[mt] = (p < a.P) ? a.Ct + (size_t)p * a.ld : nullptr;
+  }
+
+  double R[MT][NT][2], S[NT][NT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) { R[mt][nt][0] = 0; R[mt][nt][1] = 0; }
+#pragma unroll
+  for (int n1 = 0; n1 < NT; n1++)
+#pragma unroll
+    for (int n2 = 0; n2 < NT; n2++) { S[n1][n2][0] = 0; S[n1][n2][1] = 0; }
+
+  const int n_chunks = a.ld >> 3;
+  const int wstride = gridDim.x * ST_WARPS;
+  for (int ch = blockIdx.x * ST_WARPS + warp; ch < n_chunks; ch += wstride) {
+    const int i = (ch << 3) + 2 * c;
+    double2 av[MT], wv[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) av[mt] = ap[mt] ? ld2_stream(ap[mt] + i) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      double2 w = make_double2(0.0, 0.0);
+      if (zp[nt]) {
+        w = ld2(zp[nt] + i);
+        if (cp[nt]) { double2 t = ld2(cp[nt] + i); w.x *= t.x; w.y *= t.y; }
+        if (xp[nt]) { double2 t = ld2(xp[nt] + i); w.x *= t.x; w.y *= t.y; }
+      }
+      wv[nt] = w;
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        dmma884(R[mt][nt][0], R[mt][nt][1], av[mt].x, wv[nt].x);
+        dmma884(R[mt][nt][0], R[mt][nt][1], av[mt].y, wv[nt].y);
+      }
+    if (do_wtw) {
+#pragma unroll
+      for (int n1 = 0; n1 < NT; n1++)
+#pragma unroll
+        for (int n2 = n1; n2 < NT; n2++) {
+          dmma884(S[n1][n2][0], S[n1][n2][1], wv[n1].x, wv[n2].x);
+          dmma884(S[n1][n2][0], S[n1][n2][1], wv[n1].y, wv[n2].y);
+        }
+    }
+  }
+
+  // block reduction: warps add their fragments into shared memory one after the other (fixed order)
+  for (int w = 0; w < ST_WARPS; w++) {
+    if (warp == w) {
+      int t = 0;
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++, t++) {
+          int idx = t * 64 + g * 8 + 2 * c;
+          if (w == 0) { s_acc[idx] = R[mt][nt][0]; s_acc[idx + 1] = R[mt][nt][1]; }
+          else { s_acc[idx] += R[mt][nt][0]; s_acc[idx + 1] += R[mt][nt][1]; }
+        }
+#pragma unroll
+      for (int n1 = 0; n1 < NT; n1++)
+#pragma unroll
+        for (int n2 = 0; n2 < NT; n2++, t++) {
+          int idx = t * 64 + g * 8 + 2 * c;
+          if (w == 0) { s_acc[idx] = S[n1][n2][0]; s_acc[idx + 1] = S[n1][n2][1]; }
+          else { s_acc[idx] += S[n1][n2][0]; s_acc[idx + 1] += S[n1][n2][1]; }
+        }
+    }
+    __syncthreads();
+  }
+  double* row = a.partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (TILES * 64);
+  for (int idx = threadIdx.x; idx < TILES * 64; idx += ST_THREADS) row[idx] = s_acc[idx];
+}
+
+// second stage: one thread per output element sums the block partials in block order
+template <int MT, int NT>
+__global__ void stats_final_kernel(const StatsArgs a, int gx) {
+  constexpr int TILES = MT * NT + NT * NT;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nR = a.P * a.q, nS = a.q * a.q;
+  if (e >= nR + nS) return;
+  int by, idx;
+  if (e < nR) {
+    int p = e % a.P, f = e / a.P;
+    int mtg = p >> 3;
+    by = mtg / MT;
+    idx = ((mtg % MT) * NT + (f >> 3)) * 64 + (p & 7) * 8 + (f & 7);
+  } else {
+    int s = e - nR;
+    int f1 = s % a.q, f2 = s / a.q;
+    if (f1 > f2) { int t = f1; f1 = f2; f2 = t; }     // only tiles n1 <= n2 are accumulated
+    by = 0;
+    idx = (MT * NT + (f1 >> 3) * NT + (f2 >> 3)) * 64 + (f1 & 7) * 8 + (f2 & 7);
+  }
+  const double* base = a.partials + (size_t)by * gx * (TILES * 64) + idx;
+  double t = 0;
+  for (int b = 0; b < gx; b++) t += base[(size_t)b * (TILES * 64)];
+  if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t;
+}
+
+int stats_blocks(int sm_count) { return sm_count * 4; }
+
+static inline void stats_shape(int P, int q, int& MT, int& NT, int& gy) {
+  NT = (q + 7) / 8;
+  int mtiles = (P + 7) / 8;
+  MT = mtiles < 4 ? mtiles : 4;
+  if (NT >= 4 && MT > 2) MT = 2;     // keep the accumulator file within the register budget
+  gy = (mtiles + MT - 1) / MT;
+}
+
+size_t stats_partial_doubles(int P, int q, int blocks) {
+  int MT, NT, gy;
+  stats_shape(P, q, MT, NT, gy);
+  return (size_t)gy * blocks * (MT * NT + NT * NT) * 64;
+}
+
+template <int MT, int NT>
+static int launch_stats_t(const StatsArgs& a, int gy, cudaStream_t s) {
+  dim3 grid(a.blocks, gy);
+  stats_kernel<MT, NT><<<grid, ST_THREADS, 0, s>>>(a);
+  int tot = a.P * a.q + a.q * a.q;
+  stats_final_kernel<MT, NT><<<(tot + 127) / 128, 128, 0, s>>>(a, a.blocks);
+  g_launch_count += 2;
+  return (int)cudaGetLastError();
+}
+
+int launch_stats(const StatsArgs& a, cudaStream_t s) {
+  int MT, NT, gy;
+  stats_shape(a.P, a.q, MT, NT, gy);
+#define BF_ST(M_, N_) if (MT == M_ && NT == N_) return launch_stats_t<M_, N_>(a, gy, s);
+  BF_ST(1, 1) BF_ST(2, 1) BF_ST(3, 1) BF_ST(4, 1)
+  BF_ST(1, 2) BF_ST(2, 2) BF_ST(3, 2) BF_ST(4, 2)
+  BF_ST(1, 3) BF_ST(2, 3) BF_ST(3, 3) BF_ST(4, 3)
+  BF_ST(1, 4) BF_ST(2, 4)
+  BF_ST(1, 5) BF_ST(2, 5)
+  BF_ST(1, 6) BF_ST(2, 6)
+#undef BF_ST
+  return -3;
+}
+
+}  // namespace bf

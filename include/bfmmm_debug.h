@@ -1,0 +1,21 @@
+/* bfmmm_debug.h -- diagnostics entry points of libbfmmm_b200.so used by the parity tests only.
+ * They are not part of the drop-in boundary (include/bfmmm.h). */
+#ifndef BFMMM_DEBUG_H
+#define BFMMM_DEBUG_H
+#include "bfmmm.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* keep / return the per-function Metropolis log acceptance ratio of bfmmm_update_z */
+int bfmmm_debug_enable_acc(bfmmm_engine* e, int on);
+int bfmmm_debug_get_acc(bfmmm_engine* e, double* acc /* n */);
+/* device-RNG updates that also return the draws they used (to replay them through the oracle) */
+int bfmmm_debug_update_z_rng(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta,
+                             double* gam_out /* n x K */, double* u_out /* n */);
+int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out /* n x M */);
+/* the projected cache: whitened coefficients (n x P column-major) and orthogonal residual norms */
+int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss);
+#ifdef __cplusplus
+}
+#endif
+#endif
