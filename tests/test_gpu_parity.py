@@ -25,9 +25,12 @@ def test_update_z(name, beta):
     # the acceptance log-ratio is a difference of O(a_Z_PM log a_Z_PM) lgamma terms: scale the
     # tolerance by the magnitude of those terms (1e-10 relative to what was actually summed)
     scale = 1.0 + np.abs(acc_o) + cases.A_Z_PM * np.log(cases.A_Z_PM) * 1e-3
-    assert np.max(np.abs(acc_g - acc_o) / scale) < TOL
+    # a proposal coordinate that underflows to 0 makes the reference's ratio NaN (=> reject): same here
+    assert np.array_equal(np.isnan(acc_g), np.isnan(acc_o))
+    fin = ~np.isnan(acc_o)
+    assert np.max(np.abs(acc_g[fin] - acc_o[fin]) / scale[fin]) < TOL
     margin = np.abs(np.log(dr["u"]) - acc_o)
-    decided = margin > 1e-8          # knife-edge decisions may legitimately differ
+    decided = ~(margin <= 1e-8)      # knife-edge decisions may legitimately differ
     assert np.array_equal(Zg[decided], Zo[decided])
     assert nacc == int(took.sum()) or not decided.all()
     assert rel(slz, np.log(Zo).sum(axis=0)) < TOL
@@ -137,8 +140,9 @@ def test_device_rng_replay(name):
     Zo, acc_o, _ = orc.update_z(d, st, s["pi"], 1.3, cases.A_Z_PM, gam, u)
     decided = np.abs(np.log(u) - acc_o) > 1e-8
     assert np.array_equal(Zg[decided], Zo[decided])
-    assert np.all((u > 0) & (u < 1)) and np.all(gam > 0)
-    zscore = (gam - cases.A_Z_PM * s["Z"]) / np.sqrt(cases.A_Z_PM * s["Z"])
+    assert np.all((u > 0) & (u < 1)) and np.all(gam >= 0)     # tiny shapes may underflow to 0, as in R
+    big = cases.A_Z_PM * s["Z"] > 5
+    zscore = ((gam - cases.A_Z_PM * s["Z"]) / np.sqrt(cases.A_Z_PM * s["Z"]))[big]
     assert abs(zscore.mean()) < 5 / np.sqrt(zscore.size) and 0.7 < zscore.std() < 1.3
     # chi with device normals
     eng.set_state(s["Z"], s["chi"])
