@@ -6,5 +6,6 @@ There is no CPU fallback: importing works anywhere, creating an Engine needs the
 """
 from ._lib import load_library, library_path, build_library  # noqa: F401
 from .engine import Engine, EngineError  # noqa: F401
+from .sampler import Sampler, default_hyper, SWEEP_THETA, SWEEP_NU_Z, SWEEP_FULL  # noqa: F401
 
-__all__ = ["Engine", "EngineError", "load_library", "library_path", "build_library"]
+__all__ = ["Engine", "EngineError", "Sampler", "default_hyper", "SWEEP_THETA", "SWEEP_NU_Z", "SWEEP_FULL", "load_library", "library_path", "build_library"]

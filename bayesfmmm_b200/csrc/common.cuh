@@ -204,4 +204,5 @@ int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots,
                    double* B_rowmajor, cudaStream_t s);
 
 extern unsigned long long g_launch_count;
+int set_error(const char* msg);   // records the message returned by bfmmm_last_error(); returns 1
 }  // namespace bf

@@ -16,6 +16,9 @@ namespace bf { unsigned long long g_launch_count = 0; }
 namespace {
 thread_local std::string g_err;
 int fail(const std::string& m) { g_err = m; return 1; }
+}
+namespace bf { int set_error(const char* msg) { g_err = msg; return 1; } }
+namespace {
 #define CU(x)                                                                          \
   do {                                                                                 \
     cudaError_t _e = (x);                                                              \
@@ -265,6 +268,17 @@ void bfmmm_destroy(bfmmm_engine* e) { free_all(e); }
 int bfmmm_get_basis(bfmmm_engine* e, double* B_out) {
   if (!e || e->identity) return fail("bfmmm_get_basis: no basis for this model");
   std::copy(e->B.begin(), e->B.end(), B_out);
+  return 0;
+}
+int bfmmm_engine_dims(bfmmm_engine* e, int32_t* dims) {
+  if (!e || !dims) return fail("null argument");
+  dims[0] = e->n; dims[1] = e->K; dims[2] = e->P; dims[3] = e->M; dims[4] = e->D; dims[5] = e->model;
+  return 0;
+}
+int bfmmm_counts(bfmmm_engine* e, double* sum_half, double* n_points) {
+  if (!e) return fail("null engine");
+  if (sum_half) *sum_half = e->sum_half;
+  if (n_points) *n_points = e->n_points;
   return 0;
 }
 int bfmmm_get_gram(bfmmm_engine* e, double* G) {

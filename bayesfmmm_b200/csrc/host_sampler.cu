@@ -1,0 +1,803 @@
+// host_sampler.cu -- the host loop above the engine ABI (include/bfmmm_sampler.h): the
+// reference's driver loops restated without Rcpp/Armadillo.  Pure host C++ (compiled by nvcc
+// only so that it shares common.cuh's Philox generator with the device code).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/bfmmm_sampler.h"
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ host random numbers
+// purposes of the global Philox streams (one stream per purpose and iteration)
+enum { HP_PI = 101, HP_ALPHA3, HP_PHI, HP_DELTA, HP_A, HP_GAMMA, HP_NU, HP_TAU, HP_SIGMA, HP_ETA, HP_XI,
+       HP_TAU_ETA, HP_DELTA_XI, HP_A_XI, HP_GAMMA_XI };
+
+struct HostRng {
+  uint64_t key = 0, iteration = 0;
+  std::deque<double> tape;
+  bool use_tape = false;
+  bf::RngStream stream{0, 0, 0, 0};
+  void open(uint32_t purpose) { stream = bf::RngStream(key, 0xB200ull, iteration, purpose); }
+  bool taped() { return use_tape; }
+  double pop() {
+    if (tape.empty()) return std::numeric_limits<double>::quiet_NaN();
+    double v = tape.front(); tape.pop_front(); return v;
+  }
+  double normal() { return use_tape ? pop() : stream.normal(); }
+  double uniform() { return use_tape ? pop() : stream.uniform(); }
+  double gamma(double shape) { return use_tape ? pop() : stream.gamma(shape); }   // Gamma(shape, 1)
+};
+
+// ------------------------------------------------------------------ small dense linear algebra (column-major)
+using vecd = std::vector<double>;
+
+bool chol_lower(int n, const double* A, double* L) {
+  std::fill(L, L + (size_t)n * n, 0.0);
+  for (int j = 0; j < n; j++) {
+    double s = A[(size_t)j * n + j];
+    for (int k = 0; k < j; k++) s -= L[(size_t)k * n + j] * L[(size_t)k * n + j];
+    if (!(s > 0)) return false;
+    double d = std::sqrt(s);
+    L[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      double t = A[(size_t)j * n + i];
+      for (int k = 0; k < j; k++) t -= L[(size_t)k * n + i] * L[(size_t)k * n + j];
+      L[(size_t)j * n + i] = t / d;
+    }
+  }
+  return true;
+}
+
+// inverse of a symmetric positive definite matrix through its Cholesky factor: A = R R',
+// A^{-1} = R^{-T} R^{-1} (symmetric by construction)
+bool inv_spd(int n, const double* A, double* Ainv, vecd& work) {
+  work.resize((size_t)2 * n * n);
+  double* R = work.data();
+  double* Ri = work.data() + (size_t)n * n;
+  if (!chol_lower(n, A, R)) return false;
+  std::fill(Ri, Ri + (size_t)n * n, 0.0);
+  for (int c = 0; c < n; c++) {                 // Ri = R^{-1} (lower), column by column
+    Ri[(size_t)c * n + c] = 1.0 / R[(size_t)c * n + c];
+    for (int i = c + 1; i < n; i++) {
+      double s = 0;
+      for (int k = c; k < i; k++) s += R[(size_t)k * n + i] * Ri[(size_t)c * n + k];
+      Ri[(size_t)c * n + i] = -s / R[(size_t)i * n + i];
+    }
+  }
+  for (int c = 0; c < n; c++)
+    for (int r = c; r < n; r++) {
+      double s = 0;
+      for (int k = r; k < n; k++) s += Ri[(size_t)r * n + k] * Ri[(size_t)c * n + k];
+      Ainv[(size_t)c * n + r] = s;
+      Ainv[(size_t)r * n + c] = s;
+    }
+  return true;
+}
+
+// pseudo-inverse of a symmetric matrix (cyclic Jacobi); used when the precision is singular
+void pinv_sym_jacobi(int n, const double* A, double* Ainv) {
+  vecd a(A, A + (size_t)n * n), V((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0;
+    for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) off += a[(size_t)q * n + p] * a[(size_t)q * n + p];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = a[(size_t)q * n + p];
+        if (apq == 0.0) continue;
+        double theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < n; k++) { double x = a[(size_t)p * n + k], y = a[(size_t)q * n + k]; a[(size_t)p * n + k] = c * x - s * y; a[(size_t)q * n + k] = s * x + c * y; }
+        for (int k = 0; k < n; k++) { double x = a[(size_t)k * n + p], y = a[(size_t)k * n + q]; a[(size_t)k * n + p] = c * x - s * y; a[(size_t)k * n + q] = s * x + c * y; }
+        for (int k = 0; k < n; k++) { double x = V[(size_t)p * n + k], y = V[(size_t)q * n + k]; V[(size_t)p * n + k] = c * x - s * y; V[(size_t)q * n + k] = s * x + c * y; }
+      }
+  }
+  double lmax = 0;
+  for (int i = 0; i < n; i++) lmax = std::max(lmax, std::fabs(a[(size_t)i * n + i]));
+  double tol = n * lmax * std::numeric_limits<double>::epsilon();
+  std::fill(Ainv, Ainv + (size_t)n * n, 0.0);
+  for (int e = 0; e < n; e++) {
+    double lam = a[(size_t)e * n + e];
+    if (std::fabs(lam) <= tol) continue;
+    for (int j = 0; j < n; j++) {
+      double vj = V[(size_t)e * n + j] / lam;
+      for (int i = 0; i < n; i++) Ainv[(size_t)j * n + i] += V[(size_t)e * n + i] * vj;
+    }
+  }
+}
+
+double lgamma_d(double x) { return std::lgamma(x); }
+double pnorm_std(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
+double qnorm_std(double p) {          // Acklam's rational approximation + Halley refinement
+  if (p <= 0) return -std::numeric_limits<double>::infinity();
+  if (p >= 1) return std::numeric_limits<double>::infinity();
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                             1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                             6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                             -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                             3.754408661907416e+00};
+  double q, r, x;
+  if (p < 0.02425) { q = std::sqrt(-2 * std::log(p));
+    x = (((((c[0]*q+c[1])*q+c[2])*q+c[3])*q+c[4])*q+c[5]) / ((((d[0]*q+d[1])*q+d[2])*q+d[3])*q+1);
+  } else if (p <= 1 - 0.02425) { q = p - 0.5; r = q * q;
+    x = (((((a[0]*r+a[1])*r+a[2])*r+a[3])*r+a[4])*r+a[5])*q / (((((b[0]*r+b[1])*r+b[2])*r+b[3])*r+b[4])*r+1);
+  } else { q = std::sqrt(-2 * std::log(1 - p));
+    x = -(((((c[0]*q+c[1])*q+c[2])*q+c[3])*q+c[4])*q+c[5]) / ((((d[0]*q+d[1])*q+d[2])*q+d[3])*q+1);
+  }
+  for (int it = 0; it < 2; it++) {
+    double e = pnorm_std(x) - p;
+    double u = e * std::sqrt(2 * 3.14159265358979323846) * std::exp(x * x / 2);
+    x = x - u / (1 + x * u / 2);
+  }
+  return x;
+}
+// truncated normal on [lo, inf): inverse-CDF draw from one uniform; log density
+double rtruncnorm_lo(double mean, double sd, double lo, double u) {
+  double pa = pnorm_std((lo - mean) / sd);
+  return mean + sd * qnorm_std(pa + u * (1.0 - pa));
+}
+double dtruncnorm_lo_log(double x, double mean, double sd, double lo) {
+  if (x < lo) return -std::numeric_limits<double>::infinity();
+  const double LN_SQRT_2PI = 0.918938533204672741780329736406;
+  double z = (x - mean) / sd;
+  double scale = 1.0 - pnorm_std((lo - mean) / sd);
+  return -(LN_SQRT_2PI + 0.5 * z * z + std::log(sd)) - std::log(scale);
+}
+
+int sfail(const std::string& m) { return bf::set_error(m.c_str()); }
+
+}  // namespace
+
+struct bfmmm_sampler {
+  bfmmm_engine* e = nullptr;
+  bfmmm_hyper h{};
+  int n = 0, K = 0, P = 0, M = 0, D = 0, q = 0;
+  bool identity = false;
+  int64_t n_total = 0, iteration = 0, last_accept = 0;
+  double sum_half_total = 0, n_points_total = 0;   // sum_i floor(n_i/2) and sum_i n_i over ALL shards
+  HostRng rng;
+  bfmmm_allreduce_fn allreduce = nullptr;
+  void* allreduce_ctx = nullptr;
+  // current values (Armadillo layouts)
+  vecd nu, Phi, pi, delta, gamma, A, tau, eta, xi, tau_eta, delta_xi, gamma_xi, A_xi, Pmat, G;
+  double sigma_sq = 1.0, alpha3 = 1.0, loglik = 0.0;
+  vecd stats;     // host copy of the engine statistics buffer
+  vecd work, Prec, C, Lc, rhs, v1, v2;
+
+  double& nu_(int k, int p) { return nu[(size_t)p * K + k]; }
+  double& Phi_(int k, int p, int m) { return Phi[((size_t)m * P + p) * K + k]; }
+  double& eta_(int p, int d, int k) { return eta[((size_t)k * D + d) * P + p]; }
+  double& xi_(int k, int p, int d, int m) { return xi[(size_t)k * P * D * M + ((size_t)m * D + d) * P + p]; }
+  double& gamma_(int k, int p, int m) { return gamma[((size_t)m * P + p) * K + k]; }
+  double& gamma_xi_(int k, int p, int d, int m) { return gamma_xi[(size_t)k * P * D * M + ((size_t)m * D + d) * P + p]; }
+  double& delta_(int k, int m) { return delta[(size_t)m * K + k]; }
+  double& delta_xi_(int k, int m, int d) { return delta_xi[((size_t)d * M + m) * K + k]; }
+  double& A_(int k, int i) { return A[(size_t)i * K + k]; }
+  double& A_xi_(int k, int i, int d) { return A_xi[((size_t)d * 2 + i) * K + k]; }
+  double& tau_eta_(int k, int d) { return tau_eta[(size_t)d * K + k]; }
+  int feat(int k, int mm, int dd) const { return (k * (M + 1) + mm) * (1 + D) + dd; }
+};
+
+namespace {
+
+// coefficient vector of feature f (length P) read from / written to the sampler state
+void get_coef(bfmmm_sampler* s, int k, int mm, int dd, double* out) {
+  for (int p = 0; p < s->P; p++) {
+    if (mm == 0 && dd == 0) out[p] = s->nu_(k, p);
+    else if (mm == 0) out[p] = s->eta_(p, dd - 1, k);
+    else if (dd == 0) out[p] = s->Phi_(k, p, mm - 1);
+    else out[p] = s->xi_(k, p, dd - 1, mm - 1);
+  }
+}
+void set_coef(bfmmm_sampler* s, int k, int mm, int dd, const double* in) {
+  for (int p = 0; p < s->P; p++) {
+    if (mm == 0 && dd == 0) s->nu_(k, p) = in[p];
+    else if (mm == 0) s->eta_(p, dd - 1, k) = in[p];
+    else if (dd == 0) s->Phi_(k, p, mm - 1) = in[p];
+    else s->xi_(k, p, dd - 1, mm - 1) = in[p];
+  }
+}
+
+// One Gaussian block draw from the sufficient statistics:
+//   Prec = beta * S_aa * G / sigma^2 + Prior,   rhs = beta * (g_a - G * sum_{b != a} S_ab c_b) / sigma^2
+//   C = pinv(Prec) symmetrised (nu, eta: UpdateNu.h:67-68) or inv(Prec) (Phi, xi: UpdatePhi.h:79)
+//   draw = C rhs + chol_lower(C) z                                (arma::mvnrnd, UpdateNu.h:69)
+int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const double* BtYW, double beta,
+               const double* prior_full, const double* prior_diag) {
+  const int P = s->P, q = s->q;
+  const int a = s->feat(k, mm, dd);
+  s->Prec.resize((size_t)P * P); s->C.resize((size_t)P * P); s->Lc.resize((size_t)P * P);
+  s->rhs.resize(P); s->v1.resize(P); s->v2.resize(P);
+  // v1 = sum_{b != a} S_ab c_b
+  std::fill(s->v1.begin(), s->v1.end(), 0.0);
+  for (int kk = 0; kk < s->K; kk++)
+    for (int m2 = 0; m2 <= s->M; m2++)
+      for (int d2 = 0; d2 <= s->D; d2++) {
+        int b = s->feat(kk, m2, d2);
+        if (b == a) continue;
+        double sab = WtW[(size_t)b * q + a];
+        if (sab == 0.0) continue;
+        get_coef(s, kk, m2, d2, s->v2.data());
+        for (int p = 0; p < P; p++) s->v1[p] += sab * s->v2[p];
+      }
+  const double saa = WtW[(size_t)a * q + a];
+  const double sc = beta / s->sigma_sq;
+  for (int r = 0; r < P; r++) {
+    double gv = 0;
+    if (s->identity) gv = s->v1[r];
+    else for (int c = 0; c < P; c++) gv += s->G[(size_t)c * P + r] * s->v1[c];
+    s->rhs[r] = sc * (BtYW[(size_t)a * P + r] - gv);
+  }
+  for (int c = 0; c < P; c++)
+    for (int r = 0; r < P; r++) {
+      double g = s->identity ? (r == c ? 1.0 : 0.0) : s->G[(size_t)c * P + r];
+      double pr = prior_full ? prior_full[(size_t)c * P + r] : (r == c ? prior_diag[r] : 0.0);
+      s->Prec[(size_t)c * P + r] = sc * saa * g + pr;
+    }
+  if (!inv_spd(P, s->Prec.data(), s->C.data(), s->work)) {
+    pinv_sym_jacobi(P, s->Prec.data(), s->C.data());
+    for (int c = 0; c < P; c++)
+      for (int r = c + 1; r < P; r++) {
+        double t = (s->C[(size_t)c * P + r] + s->C[(size_t)r * P + c]) / 2;
+        s->C[(size_t)c * P + r] = t; s->C[(size_t)r * P + c] = t;
+      }
+  }
+  if (!chol_lower(P, s->C.data(), s->Lc.data())) return sfail("block draw: covariance is not positive definite");
+  for (int p = 0; p < P; p++) s->v2[p] = s->rng.normal();
+  for (int r = 0; r < P; r++) {
+    double mean = 0, dev = 0;
+    for (int c = 0; c < P; c++) mean += s->C[(size_t)c * P + r] * s->rhs[c];
+    for (int c = 0; c <= r; c++) dev += s->Lc[(size_t)c * P + r] * s->v2[c];
+    s->v1[r] = mean + dev;
+  }
+  set_coef(s, k, mm, dd, s->v1.data());
+  return 0;
+}
+
+double calc_lB(const double* al, int K) {
+  double lB = 0, tot = 0;
+  for (int k = 0; k < K; k++) { lB += lgamma_d(al[k]); tot += al[k]; }
+  return lB - lgamma_d(tot);
+}
+
+int push_globals(bfmmm_sampler* s) {
+  return bfmmm_set_globals(s->e, s->nu.data(), s->Phi.data(), s->D ? s->eta.data() : nullptr,
+                           s->D ? s->xi.data() : nullptr, s->sigma_sq);
+}
+
+int reduce_and_read(bfmmm_sampler* s) {
+  double* dev = nullptr; int64_t len = 0;
+  if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
+  if (s->allreduce) {
+    if (s->allreduce(s->allreduce_ctx, dev, len, bfmmm_stream(s->e))) return sfail("all-reduce hook failed");
+  }
+  s->stats.resize(len);
+  return bfmmm_read_stats(s->e, s->stats.data(), len);
+}
+const double* st_slz(bfmmm_sampler* s) { return s->stats.data(); }
+double st_acc(bfmmm_sampler* s) { return s->stats[s->K]; }
+double st_ssr(bfmmm_sampler* s) { return s->stats[s->K + 1]; }
+double st_ssr_after(bfmmm_sampler* s) { return s->stats[s->K + 2]; }
+const double* st_wtw(bfmmm_sampler* s) { return s->stats.data() + s->K + 3; }
+const double* st_btyw(bfmmm_sampler* s) { return s->stats.data() + s->K + 3 + (size_t)s->q * s->q; }
+
+}  // namespace
+
+extern "C" {
+
+void bfmmm_hyper_defaults(bfmmm_hyper* h, int theta_est_defaults) {
+  for (int k = 0; k < 8; k++) h->c[k] = 10.0;
+  h->b = 10; h->nu_1 = 3;
+  if (theta_est_defaults) { h->alpha1l = 2; h->alpha2l = 3; h->beta1l = 2; h->beta2l = 2; }   // UserFunctions.cpp:700-703
+  else { h->alpha1l = 1; h->alpha2l = 2; h->beta1l = 1; h->beta2l = 1; }                      // :179-182
+  h->a_Z_PM = 10000; h->a_pi_PM = 1000; h->var_alpha3 = 0.05; h->var_epsilon1 = 1; h->var_epsilon2 = 1;
+  h->alpha_nu = 10; h->beta_nu = 1; h->alpha_eta = 10; h->beta_eta = 1; h->alpha_0 = 1; h->beta_0 = 1;
+}
+
+static bfmmm_sampler* make_sampler(const int32_t* dims, const bfmmm_hyper* h, int64_t n_total, uint64_t seed) {
+  bfmmm_sampler* s = new bfmmm_sampler();
+  s->h = *h;
+  s->n = dims[0]; s->K = dims[1]; s->P = dims[2]; s->M = dims[3]; s->D = dims[4];
+  s->identity = dims[5] == BFMMM_MULTIVARIATE;
+  s->q = s->K * (1 + s->D) * (1 + s->M);
+  s->n_total = n_total > 0 ? n_total : s->n;
+  s->rng.key = seed;
+  const int K = s->K, P = s->P, M = s->M, D = s->D;
+  s->nu.assign((size_t)K * P, 0.0); s->Phi.assign((size_t)K * P * M, 0.0);
+  s->pi.assign(K, 1.0 / K); s->delta.assign((size_t)K * M, 1.0); s->gamma.assign((size_t)K * P * M, 1.0);
+  s->A.assign((size_t)K * 2, 1.0); s->tau.assign(K, 1.0);
+  if (D) {
+    s->eta.assign((size_t)P * D * K, 0.0); s->xi.assign((size_t)K * P * D * M, 0.0);
+    s->tau_eta.assign((size_t)K * D, 1.0); s->delta_xi.assign((size_t)K * M * D, 1.0);
+    s->gamma_xi.assign((size_t)K * P * D * M, 1.0); s->A_xi.assign((size_t)K * 2 * D, 1.0);
+  }
+  s->G.assign((size_t)P * P, 0.0);
+  return s;
+}
+
+int bfmmm_sampler_create(bfmmm_engine* e, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
+                         uint64_t seed, bfmmm_sampler** out) {
+  if (!e || !h || !out) return sfail("bfmmm_sampler_create: null argument");
+  int32_t dims[6];
+  if (bfmmm_engine_dims(e, dims)) return 1;
+  if (dims[5] != BFMMM_MULTIVARIATE && !Pmat) return sfail("bfmmm_sampler_create: the functional model needs the penalty matrix P");
+  bfmmm_sampler* s = make_sampler(dims, h, n_total, seed);
+  s->e = e;
+  bfmmm_get_gram(e, s->G.data());
+  if (Pmat) s->Pmat.assign(Pmat, Pmat + (size_t)s->P * s->P);
+  double sum_half = 0, npts = 0;
+  bfmmm_counts(e, &sum_half, &npts);
+  // per-shard counts -> whole data set (common grid: every function has the same n_i)
+  double ratio = (double)s->n_total / (double)s->n;
+  s->n_points_total = npts * ratio;
+  s->sum_half_total = s->identity ? (double)(((int64_t)s->n_total * s->P) / 2) : sum_half * ratio;
+  *out = s;
+  return 0;
+}
+
+// sampler without an engine: only the bfmmm_host_update_* functions may be called on it (CPU tests)
+int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
+                                  const double* G, double sum_half_total, double n_points_total, uint64_t seed,
+                                  bfmmm_sampler** out) {
+  if (!dims || !h || !out) return sfail("bfmmm_sampler_create_detached: null argument");
+  bfmmm_sampler* s = make_sampler(dims, h, n_total, seed);
+  if (G) s->G.assign(G, G + (size_t)s->P * s->P);
+  if (Pmat) s->Pmat.assign(Pmat, Pmat + (size_t)s->P * s->P);
+  s->sum_half_total = sum_half_total; s->n_points_total = n_points_total;
+  *out = s;
+  return 0;
+}
+void bfmmm_sampler_destroy(bfmmm_sampler* s) { delete s; }
+int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx) {
+  if (!s) return sfail("null sampler");
+  s->allreduce = fn; s->allreduce_ctx = ctx;
+  return 0;
+}
+
+#define CP_IN(dst, src) if (src) std::copy(src, src + (dst).size(), (dst).begin())
+#define CP_OUT(dst, src) if (dst) std::copy((src).begin(), (src).end(), dst)
+int bfmmm_sampler_set(bfmmm_sampler* s, const double* nu, const double* Phi, const double* sigma_sq,
+                      const double* pi, const double* alpha3, const double* delta, const double* gamma,
+                      const double* A, const double* tau) {
+  if (!s) return sfail("null sampler");
+  CP_IN(s->nu, nu); CP_IN(s->Phi, Phi); CP_IN(s->pi, pi); CP_IN(s->delta, delta); CP_IN(s->gamma, gamma);
+  CP_IN(s->A, A); CP_IN(s->tau, tau);
+  if (sigma_sq) s->sigma_sq = *sigma_sq;
+  if (alpha3) s->alpha3 = *alpha3;
+  return 0;
+}
+int bfmmm_sampler_get(bfmmm_sampler* s, double* nu, double* Phi, double* sigma_sq, double* pi,
+                      double* alpha3, double* delta, double* gamma, double* A, double* tau, double* loglik) {
+  if (!s) return sfail("null sampler");
+  CP_OUT(nu, s->nu); CP_OUT(Phi, s->Phi); CP_OUT(pi, s->pi); CP_OUT(delta, s->delta); CP_OUT(gamma, s->gamma);
+  CP_OUT(A, s->A); CP_OUT(tau, s->tau);
+  if (sigma_sq) *sigma_sq = s->sigma_sq;
+  if (alpha3) *alpha3 = s->alpha3;
+  if (loglik) *loglik = s->loglik;
+  return 0;
+}
+int bfmmm_sampler_set_cov(bfmmm_sampler* s, const double* eta, const double* xi, const double* tau_eta,
+                          const double* delta_xi, const double* gamma_xi, const double* A_xi) {
+  if (!s || !s->D) return sfail("sampler has no covariates");
+  CP_IN(s->eta, eta); CP_IN(s->xi, xi); CP_IN(s->tau_eta, tau_eta); CP_IN(s->delta_xi, delta_xi);
+  CP_IN(s->gamma_xi, gamma_xi); CP_IN(s->A_xi, A_xi);
+  return 0;
+}
+int bfmmm_sampler_get_cov(bfmmm_sampler* s, double* eta, double* xi, double* tau_eta, double* delta_xi,
+                          double* gamma_xi, double* A_xi) {
+  if (!s || !s->D) return sfail("sampler has no covariates");
+  CP_OUT(eta, s->eta); CP_OUT(xi, s->xi); CP_OUT(tau_eta, s->tau_eta); CP_OUT(delta_xi, s->delta_xi);
+  CP_OUT(gamma_xi, s->gamma_xi); CP_OUT(A_xi, s->A_xi);
+  return 0;
+}
+int bfmmm_sampler_tape(bfmmm_sampler* s, const double* values, int64_t n) {
+  if (!s) return sfail("null sampler");
+  s->rng.use_tape = true;
+  for (int64_t i = 0; i < n; i++) s->rng.tape.push_back(values[i]);
+  return 0;
+}
+int64_t bfmmm_sampler_tape_left(bfmmm_sampler* s) { return s ? (int64_t)s->rng.tape.size() : -1; }
+int64_t bfmmm_sampler_iteration(bfmmm_sampler* s) { return s ? s->iteration : -1; }
+int64_t bfmmm_sampler_last_accept(bfmmm_sampler* s) { return s ? s->last_accept : -1; }
+
+// ================================================================= host-side updates
+// updatePi_PM (UpdatePi.h:84-116; lpdf_pi_PM :39-53 with sum_i log Z_ik from the device)
+int bfmmm_host_update_pi(bfmmm_sampler* s, const double* slz) {
+  const int K = s->K;
+  s->rng.open(HP_PI);
+  vecd al(K), prop(K), al2(K);
+  double sum = 0;
+  for (int k = 0; k < K; k++) {
+    al[k] = s->h.a_pi_PM * s->pi[k];
+    double sh = al[k] <= 0 ? 10.0 : al[k];              // rdirichlet guard, Distributions.h:24-28
+    prop[k] = s->rng.gamma(sh);
+    sum += prop[k];
+  }
+  for (int k = 0; k < K; k++) prop[k] /= sum;
+  auto lpdf = [&](const vecd& p) {
+    double l = 0;
+    vecd ap(K);
+    for (int k = 0; k < K; k++) {
+      l += (s->h.c[k] - 1) * std::log(p[k]);
+      l += (s->alpha3 * p[k] - 1) * slz[k];
+      ap[k] = s->alpha3 * p[k];
+    }
+    return l - (double)s->n_total * calc_lB(ap.data(), K);
+  };
+  auto propdens = [&](const vecd& x, const vecd& alpha) {
+    double dsum = 0;
+    for (int k = 0; k < K; k++) dsum += (alpha[k] - 1) * std::log(x[k]);
+    return dsum - calc_lB(alpha.data(), K);
+  };
+  double lnew = lpdf(prop), lold = lpdf(s->pi);
+  for (int k = 0; k < K; k++) al2[k] = s->h.a_pi_PM * prop[k];
+  double q_new = propdens(prop, al), q_old = propdens(s->pi, al2);
+  double acc = lnew - lold + q_old - q_new;
+  double u = s->rng.uniform();
+  if (std::log(u) < acc) s->pi = prop;
+  return 0;
+}
+
+// updateAlpha3 (UpdateAlpha3.h:36-63, lpdf_alpha3 :10-26)
+int bfmmm_host_update_alpha3(bfmmm_sampler* s, const double* slz) {
+  const int K = s->K;
+  s->rng.open(HP_ALPHA3);
+  const double sd = s->h.var_alpha3;
+  double prop = rtruncnorm_lo(s->alpha3, sd, 0.0, s->rng.uniform());
+  auto lpdf = [&](double a3, double a3_ph) {
+    double l = (-s->h.b) * a3;
+    vecd ap(K);
+    for (int k = 0; k < K; k++) { l += (a3 * s->pi[k] - 1) * slz[k]; ap[k] = a3 * s->pi[k]; }
+    l -= (double)s->n_total * calc_lB(ap.data(), K);
+    l += dtruncnorm_lo_log(a3_ph, a3_ph, sd, 0.0);      // as written in the reference (:23-24)
+    return l;
+  };
+  double lold = lpdf(s->alpha3, prop), lnew = lpdf(prop, s->alpha3);
+  double u = s->rng.uniform();
+  if (std::log(u) < lnew - lold) s->alpha3 = prop;
+  return 0;
+}
+
+// updateTau (UpdateTau.h:18-40) / updateTauMV (:47-68): note the integer division nu.n_cols / 2
+int bfmmm_host_update_tau(bfmmm_sampler* s) {
+  const int K = s->K, P = s->P;
+  s->rng.open(HP_TAU);
+  for (int k = 0; k < K; k++) {
+    double a = s->h.alpha_nu + (double)(P / 2);
+    double quad = 0;
+    for (int r = 0; r < P; r++) {
+      double pr = 0;
+      if (s->identity) pr = s->nu_(k, r);
+      else for (int c = 0; c < P; c++) pr += s->Pmat[(size_t)c * P + r] * s->nu_(k, c);
+      quad += s->nu_(k, r) * pr;
+    }
+    double b = s->h.beta_nu + 0.5 * quad;
+    double g = (1 / b) * s->rng.gamma(a);
+    s->tau[k] = s->identity ? 1 / g : g;
+  }
+  return 0;
+}
+
+// updateTauEta (UpdateTau.h:75-99) / updateTauEtaMV (:106-128)
+int bfmmm_host_update_tau_eta(bfmmm_sampler* s) {
+  const int K = s->K, P = s->P, D = s->D;
+  s->rng.open(HP_TAU_ETA);
+  for (int j = 0; j < K; j++)
+    for (int d = 0; d < D; d++) {
+      double a = s->h.alpha_eta + (double)(P / 2);
+      double quad = 0;
+      for (int r = 0; r < P; r++) {
+        double pr = 0;
+        if (s->identity) pr = s->eta_(r, d, j);
+        else for (int c = 0; c < P; c++) pr += s->Pmat[(size_t)c * P + r] * s->eta_(c, d, j);
+        quad += s->eta_(r, d, j) * pr;
+      }
+      double b = s->h.beta_eta + 0.5 * quad;
+      double g = (1 / b) * s->rng.gamma(a);
+      s->tau_eta_(j, d) = s->identity ? 1 / g : g;
+    }
+  return 0;
+}
+
+// updateDelta (UpdateDelta.h:17-66): multiplicative gamma process shrinkage
+int bfmmm_host_update_delta(bfmmm_sampler* s) {
+  const int K = s->K, P = s->P, M = s->M;
+  s->rng.open(HP_DELTA);
+  for (int k = 0; k < K; k++)
+    for (int i = 0; i < M; i++) {
+      double p1, p2 = 1;
+      if (i == 0) {
+        p1 = s->A_(k, 0) + ((P * M) / 2.0);
+        for (int j = 0; j < P; j++) {
+          p2 += 0.5 * s->gamma_(k, j, 0) * std::pow(s->Phi_(k, j, 0), 2.0);
+          for (int m = 1; m < M; m++) {
+            double tt = 1;
+            for (int nn = 1; nn <= m; nn++) tt *= s->delta_(k, nn);
+            p2 += 0.5 * s->gamma_(k, j, m) * tt * std::pow(s->Phi_(k, j, m), 2.0);
+          }
+        }
+      } else {
+        p1 = s->A_(k, 1) + ((P * (M - i)) / 2.0);
+        for (int j = 0; j < P; j++)
+          for (int m = i; m < M; m++) {
+            double tt = 1;
+            for (int nn = 0; nn <= m; nn++) if (nn != i) tt *= s->delta_(k, nn);
+            p2 += 0.5 * s->gamma_(k, j, m) * tt * std::pow(s->Phi_(k, j, m), 2.0);
+          }
+      }
+      s->delta_(k, i) = (1 / p2) * s->rng.gamma(p1);
+    }
+  return 0;
+}
+
+// updateDeltaXi (UpdateDelta.h:76-125)
+int bfmmm_host_update_delta_xi(bfmmm_sampler* s) {
+  const int K = s->K, P = s->P, M = s->M, D = s->D;
+  s->rng.open(HP_DELTA_XI);
+  for (int d = 0; d < D; d++)
+    for (int k = 0; k < K; k++)
+      for (int i = 0; i < M; i++) {
+        double p1, p2 = 1;
+        if (i == 0) {
+          p1 = s->A_xi_(k, 0, d) + ((P * M) * 0.5);
+          for (int j = 0; j < P; j++) {
+            p2 += 0.5 * s->gamma_xi_(k, j, d, 0) * (s->xi_(k, j, d, 0) * s->xi_(k, j, d, 0));
+            for (int m = 1; m < M; m++) {
+              double tt = 1;
+              for (int nn = 1; nn <= m; nn++) tt *= s->delta_xi_(k, nn, d);
+              p2 += 0.5 * s->gamma_xi_(k, j, d, m) * tt * (s->xi_(k, j, d, m) * s->xi_(k, j, d, m));
+            }
+          }
+        } else {
+          p1 = s->A_xi_(k, 1, d) + ((P * (M - i)) * 0.5);
+          for (int j = 0; j < P; j++)
+            for (int m = i; m < M; m++) {
+              double tt = 1;
+              for (int nn = 0; nn <= m; nn++) if (nn != i) tt *= s->delta_xi_(k, nn, d);
+              p2 += 0.5 * s->gamma_xi_(k, j, d, m) * tt * (s->xi_(k, j, d, m) * s->xi_(k, j, d, m));
+            }
+        }
+        s->delta_xi_(k, i, d) = (1 / p2) * s->rng.gamma(p1);
+      }
+  return 0;
+}
+
+// updateGamma (UpdateGamma.h:17-38)
+int bfmmm_host_update_gamma(bfmmm_sampler* s) {
+  const int K = s->K, P = s->P, M = s->M;
+  s->rng.open(HP_GAMMA);
+  const double nug = s->h.nu_1;
+  for (int i = 0; i < K; i++)
+    for (int l = 0; l < P; l++) {
+      double ph = 1;
+      for (int j = 0; j < M; j++) {
+        ph *= s->delta_(i, j);
+        double scale = 2 / (nug + ph * (s->Phi_(i, l, j) * s->Phi_(i, l, j)));
+        s->gamma_(i, l, j) = scale * s->rng.gamma((nug + 1) / 2);
+      }
+    }
+  return 0;
+}
+
+// updateGammaXi (UpdateGamma.h:48-72)
+int bfmmm_host_update_gamma_xi(bfmmm_sampler* s) {
+  const int K = s->K, P = s->P, M = s->M, D = s->D;
+  s->rng.open(HP_GAMMA_XI);
+  const double nug = s->h.nu_1;
+  for (int k = 0; k < K; k++)
+    for (int i = 0; i < D; i++)
+      for (int l = 0; l < P; l++) {
+        double ph = 1;
+        for (int j = 0; j < M; j++) {
+          ph *= s->delta_xi_(k, j, i);
+          double scale = 2 / (nug + ph * (s->xi_(k, l, i, j) * s->xi_(k, l, i, j)));
+          s->gamma_xi_(k, l, i, j) = scale * s->rng.gamma((nug + 1) / 2);
+        }
+      }
+  return 0;
+}
+
+static double lpdf_a1(double al, double be, double a, double delta) {          // UpdateA.h:17-23
+  return -std::log(std::tgamma(a)) + (a - 1) * std::log(delta) + (al - 1) * std::log(a) - (a * be);
+}
+static double lpdf_a2(double al, double be, double a, const double* delta, int M, int stride) {   // :33-44
+  double x = M - 1;
+  double l = -x * std::log(std::tgamma(a)) + (al - 1) * std::log(a) - (a * be);
+  for (int i = 1; i < M; i++) l += (a - 1) * std::log(delta[(size_t)i * stride]);
+  return l;
+}
+static void mh_a(bfmmm_sampler* s, double& a, bool first, const double* delta_row, int M, int stride) {
+  const bfmmm_hyper& h = s->h;
+  double sd = first ? h.var_epsilon1 / h.beta1l : h.var_epsilon2 / h.beta2l;
+  double cur = a;
+  double lp = first ? lpdf_a1(h.alpha1l, h.beta1l, cur, delta_row[0]) : lpdf_a2(h.alpha2l, h.beta2l, cur, delta_row, M, stride);
+  double prop = rtruncnorm_lo(cur, sd, 0.0, s->rng.uniform());
+  double lpn = first ? lpdf_a1(h.alpha1l, h.beta1l, prop, delta_row[0]) : lpdf_a2(h.alpha2l, h.beta2l, prop, delta_row, M, stride);
+  double acc = (lpn + dtruncnorm_lo_log(cur, prop, sd, 0.0)) - lp - dtruncnorm_lo_log(prop, cur, sd, 0.0);
+  double u = s->rng.uniform();
+  if (std::log(u) < acc) a = prop;
+}
+// updateA (UpdateA.h:58-135)
+int bfmmm_host_update_A(bfmmm_sampler* s) {
+  s->rng.open(HP_A);
+  for (int j = 0; j < s->K; j++)
+    for (int i = 0; i < 2; i++) mh_a(s, s->A_(j, i), i == 0, &s->delta_(j, 0), s->M, s->K);
+  return 0;
+}
+// updateAXi (UpdateA.h:137-209): order j, i, d
+int bfmmm_host_update_A_xi(bfmmm_sampler* s) {
+  s->rng.open(HP_A_XI);
+  for (int j = 0; j < s->K; j++)
+    for (int i = 0; i < 2; i++)
+      for (int d = 0; d < s->D; d++) mh_a(s, s->A_xi_(j, i, d), i == 0, &s->delta_xi_(j, 0, d), s->M, s->K);
+  return 0;
+}
+
+// updatePhi (UpdatePhi.h:23-89): blocks (j, m), prior diag(tilde_tau(j,m) * gamma(j,.,m))
+int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  const int K = s->K, P = s->P, M = s->M;
+  s->rng.open(HP_PHI);
+  vecd diag(P);
+  for (int j = 0; j < K; j++) {
+    double tt = 1;
+    for (int m = 0; m < M; m++) {
+      tt = (m == 0) ? s->delta_(j, 0) : tt * s->delta_(j, m);      // tilde_tau cumprod, BFMMM.h:1254-1259
+      for (int p = 0; p < P; p++) diag[p] = tt * s->gamma_(j, p, m);
+      if (block_draw(s, j, m + 1, 0, WtW, BtYW, beta, nullptr, diag.data())) return 1;
+    }
+  }
+  return 0;
+}
+// updateNu (UpdateNu.h:24-74): blocks j, prior tau_j * P (MV: (1/tau_j) I, :195-196)
+int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  const int K = s->K, P = s->P;
+  s->rng.open(HP_NU);
+  vecd prior((size_t)P * P), diag(P);
+  for (int j = 0; j < K; j++) {
+    if (s->identity) {
+      for (int p = 0; p < P; p++) diag[p] = 1 / s->tau[j];
+      if (block_draw(s, j, 0, 0, WtW, BtYW, beta, nullptr, diag.data())) return 1;
+    } else {
+      for (size_t e = 0; e < prior.size(); e++) prior[e] = s->tau[j] * s->Pmat[e];
+      if (block_draw(s, j, 0, 0, WtW, BtYW, beta, prior.data(), nullptr)) return 1;
+    }
+  }
+  return 0;
+}
+// updateEta (UpdateEta.h:28-94): d outer, j inner; prior tau_eta(j,d) * P (MV: (1/tau_eta) I)
+int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  const int K = s->K, P = s->P, D = s->D;
+  s->rng.open(HP_ETA);
+  vecd prior((size_t)P * P), diag(P);
+  for (int d = 0; d < D; d++)
+    for (int j = 0; j < K; j++) {
+      if (s->identity) {
+        for (int p = 0; p < P; p++) diag[p] = 1 / s->tau_eta_(j, d);
+        if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, nullptr, diag.data())) return 1;
+      } else {
+        for (size_t e = 0; e < prior.size(); e++) prior[e] = s->tau_eta_(j, d) * s->Pmat[e];
+        if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, prior.data(), nullptr)) return 1;
+      }
+    }
+  return 0;
+}
+// updateXiCovariateAdj (UpdateXi.h:26-93): order j, m, d; prior diag(tilde_tau_xi(j,m,d) * gamma_xi_j(.,d,m))
+int bfmmm_host_update_xi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  const int K = s->K, P = s->P, M = s->M, D = s->D;
+  s->rng.open(HP_XI);
+  vecd diag(P);
+  for (int j = 0; j < K; j++)
+    for (int m = 0; m < M; m++)
+      for (int d = 0; d < D; d++) {
+        double tt = 1;
+        for (int mm = 0; mm <= m; mm++) tt *= s->delta_xi_(j, mm, d);
+        for (int p = 0; p < P; p++) diag[p] = tt * s->gamma_xi_(j, p, d, m);
+        if (block_draw(s, j, m + 1, d + 1, WtW, BtYW, beta, nullptr, diag.data())) return 1;
+      }
+  return 0;
+}
+
+// updateSigma's draw (UpdateSigma.h:47-53; tempered :98-107; MV :149-151)
+int bfmmm_host_update_sigma(bfmmm_sampler* s, double ssr, double beta, int tempered) {
+  s->rng.open(HP_SIGMA);
+  double a, b1;
+  if (tempered) { a = (beta * s->n_points_total) / 2 + s->h.alpha_0; b1 = (beta / 2) * ssr + s->h.beta_0; }
+  else { a = s->sum_half_total + s->h.alpha_0; b1 = 0.5 * ssr + s->h.beta_0; }
+  double r = (1 / b1) * s->rng.gamma(a);
+  s->sigma_sq = 1 / r;
+  return 0;
+}
+
+// ================================================================= driver loops
+int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
+  if (!s) return sfail("null sampler");
+  if (!s->e) return sfail("bfmmm_sampler_step: detached sampler has no engine");
+  bfmmm_engine* e = s->e;
+  s->rng.iteration = (uint64_t)s->iteration;
+  const bool do_z = (sweep == BFMMM_SWEEP_NU_Z || sweep == BFMMM_SWEEP_FULL);
+  const bool do_phi = (sweep == BFMMM_SWEEP_THETA || sweep == BFMMM_SWEEP_FULL);
+  const bool do_nu = do_z;
+  const bool do_chi = do_phi;
+  const bool tempered = beta != 1.0;
+  if (bfmmm_seed(e, s->rng.key, (uint64_t)s->iteration)) return 1;
+  if (push_globals(s)) return 1;
+  if (do_z) {                                              // updateZ_PM -> updatePi_PM -> updateAlpha3
+    if (bfmmm_update_z_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, beta)) return 1;
+  }
+  // the sufficient statistics depend only on (Z, chi, X): one pass feeds Phi, nu, eta and xi
+  if (bfmmm_suffstats_async(e)) return 1;
+  if (reduce_and_read(s)) return 1;
+  if (do_z) {
+    s->last_accept = (int64_t)std::llround(st_acc(s));
+    if (bfmmm_host_update_pi(s, st_slz(s))) return 1;
+    if (bfmmm_host_update_alpha3(s, st_slz(s))) return 1;
+  }
+  if (do_phi) {                                            // updatePhi, updateDelta, updateA, updateGamma
+    if (bfmmm_host_update_phi(s, st_wtw(s), st_btyw(s), beta)) return 1;
+    if (bfmmm_host_update_delta(s)) return 1;
+    if (bfmmm_host_update_A(s)) return 1;
+    if (bfmmm_host_update_gamma(s)) return 1;
+  }
+  if (do_nu && bfmmm_host_update_nu(s, st_wtw(s), st_btyw(s), beta)) return 1;     // updateNu
+  if (bfmmm_host_update_tau(s)) return 1;                  // updateTau (all three loops call it)
+  // updateSigma: data pass with the new globals
+  if (push_globals(s)) return 1;
+  if (bfmmm_ssr_async(e)) return 1;
+  if (reduce_and_read(s)) return 1;
+  if (bfmmm_host_update_sigma(s, st_ssr(s), beta, tempered)) return 1;
+  double ssr_ll = st_ssr(s);
+  if (do_chi) {                                            // updateChi (+ the SSR calcLikelihood needs)
+    if (push_globals(s)) return 1;
+    if (bfmmm_update_chi_async(e, beta)) return 1;
+    if (!s->D) { if (reduce_and_read(s)) return 1; ssr_ll = st_ssr_after(s); }
+  }
+  if (s->D) {
+    // covariate-adjusted loops (BFMMM.h:3976-4000): after chi come updateEta, updateTauEta and the
+    // xi block with its shrinkage priors -- chi has changed, so the statistics are taken again
+    if (bfmmm_suffstats_async(e)) return 1;
+    if (reduce_and_read(s)) return 1;
+    if (do_nu && bfmmm_host_update_eta(s, st_wtw(s), st_btyw(s), beta)) return 1;
+    if (bfmmm_host_update_tau_eta(s)) return 1;
+    if (do_phi) {
+      if (bfmmm_host_update_xi(s, st_wtw(s), st_btyw(s), beta)) return 1;
+      if (bfmmm_host_update_delta_xi(s)) return 1;
+      if (bfmmm_host_update_A_xi(s)) return 1;
+      if (bfmmm_host_update_gamma_xi(s)) return 1;
+    }
+    if (push_globals(s)) return 1;
+    if (bfmmm_ssr_async(e)) return 1;
+    if (reduce_and_read(s)) return 1;
+    ssr_ll = st_ssr(s);
+  }
+  // calcLikelihood (CalculateLikelihood.h:19-44; MV :137-159 with floor(P/2))
+  if (s->identity)
+    s->loglik = -((double)s->n_total * (double)(s->P / 2)) * std::log(2 * 3.14159265358979323846 * s->sigma_sq) -
+                ssr_ll / (2 * s->sigma_sq);
+  else
+    s->loglik = -s->n_points_total * (0.918938533204672741780329736406 + 0.5 * std::log(s->sigma_sq)) -
+                ssr_ll / (2 * s->sigma_sq);
+  s->iteration++;
+  return 0;
+}
+
+int bfmmm_sampler_run(bfmmm_sampler* s, int sweep, int n_iter) {
+  for (int i = 0; i < n_iter; i++)
+    if (bfmmm_sampler_step(s, sweep, 1.0)) return 1;
+  return 0;
+}
+
+}  // extern "C"

@@ -103,6 +103,11 @@ int bfmmm_ssr(bfmmm_engine* e, double* ssr, double* sum_half, double* n_points);
  *   BtYW P x q   column-major  sum_i w_if B_i' y_i
  * common grid / MV only; H_fg = WtW[f,g] * (B'B).  Ragged grids: see bfmmm_suffstats_ragged. */
 int bfmmm_suffstats(bfmmm_engine* e, double* WtW, double* BtYW);
+/* shard geometry: dims = {n, K, P, M, D, model} */
+int bfmmm_engine_dims(bfmmm_engine* e, int32_t* dims);
+/* the data-only counts of updateSigma: sum_i floor(n_i/2) (UpdateSigma.h:49; MV floor(n*P/2), :150)
+ * and sum_i n_i, for this shard; no kernel launch */
+int bfmmm_counts(bfmmm_engine* e, double* sum_half, double* n_points);
 /* Gram matrix B'B (P x P, column-major) of the common basis (identity for MV). */
 int bfmmm_get_gram(bfmmm_engine* e, double* G);
 

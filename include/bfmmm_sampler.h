@@ -52,6 +52,11 @@ typedef int (*bfmmm_allreduce_fn)(void* ctx, double* buf_dev, int64_t len, void*
  * (column-major) or NULL for the multivariate model's identity prior. */
 int bfmmm_sampler_create(bfmmm_engine* e, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
                          uint64_t seed, bfmmm_sampler** out);
+/* sampler without an engine, for exercising the bfmmm_host_update_* functions on the CPU:
+ * dims = {n, K, P, M, D, model}; G = B'B (P x P) or NULL for identity */
+int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
+                                  const double* G, double sum_half_total, double n_points_total, uint64_t seed,
+                                  bfmmm_sampler** out);
 void bfmmm_sampler_destroy(bfmmm_sampler* s);
 int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx);
 

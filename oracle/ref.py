@@ -223,3 +223,35 @@ def update_A(a1l, b1l, a2l, b2l, delta, ve1, ve2, A, us):
     _done(lib().ref_update_A(K, M, C.c_double(a1l), C.c_double(b1l), C.c_double(a2l), C.c_double(b2l), _p(df),
                              C.c_double(ve1), C.c_double(ve2), _p(af), _p(out)), "update_A")
     return out
+
+
+def _cubes(x, K):
+    return np.ascontiguousarray(np.stack([np.asfortranarray(x[k]).ravel(order="F") for k in range(K)]))
+
+
+def update_delta_xi(xi, gamma_xi, A_xi, delta_xi, gdraws):
+    K, P, D, M = xi.shape
+    tape(gdraws)
+    xf, gf, af, df = _cubes(xi, K), _cubes(gamma_xi, K), _f(A_xi), _f(delta_xi)
+    out = np.zeros((K, M, D), order="F")
+    _done(lib().ref_update_delta_xi(K, P, M, D, _p(xf), _p(gf), _p(af), _p(df), _p(out)), "update_delta_xi")
+    return out
+
+
+def update_gamma_xi(nu_gamma, delta_xi, xi, gdraws):
+    K, P, D, M = xi.shape
+    tape(gdraws)
+    xf, df = _cubes(xi, K), _f(delta_xi)
+    out = np.zeros((K, P * D * M))
+    _done(lib().ref_update_gamma_xi(K, P, M, D, C.c_double(nu_gamma), _p(df), _p(xf), _p(out)), "update_gamma_xi")
+    return np.stack([out[k].reshape((P, D, M), order="F") for k in range(K)])
+
+
+def update_A_xi(a1l, b1l, a2l, b2l, delta_xi, ve1, ve2, A_xi, us):
+    K, M, D = delta_xi.shape
+    tape(us)
+    df, af = _f(delta_xi), _f(A_xi)
+    out = np.zeros((K, 2, D), order="F")
+    _done(lib().ref_update_A_xi(K, M, D, C.c_double(a1l), C.c_double(b1l), C.c_double(a2l), C.c_double(b2l), _p(df),
+                                C.c_double(ve1), C.c_double(ve2), _p(af), _p(out)), "update_A_xi")
+    return out

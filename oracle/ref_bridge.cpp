@@ -359,4 +359,42 @@ int ref_update_A(int K, int M, double a1l, double b1l, double a2l, double b2l, c
   return 0;
 }
 
+// updateDeltaXi: draws in order d, k, i.  xi/gamma_xi: K cubes P x D x M; A_xi K x 2 x D; delta K x M x D
+int ref_update_delta_xi(int K, int P, int M, int D, const double* xi, const double* gamma_xi, const double* A_xi,
+                        const double* delta_in, double* delta_out) {
+  arma::field<arma::cube> xif(1, K), gx(1, K), del(1, 1);
+  for (int k = 0; k < K; k++) {
+    xif(0, k) = cube_in(xi + (size_t)k * P * D * M, P, D, M);
+    gx(0, k) = cube_in(gamma_xi + (size_t)k * P * D * M, P, D, M);
+  }
+  del(0, 0) = cube_in(delta_in, K, M, D);
+  arma::cube ax = cube_in(A_xi, K, 2, D);
+  BayesFMMM::updateDeltaXi(xif, gx, ax, 0, 1, del);
+  cube_out(del(0, 0), delta_out);
+  return 0;
+}
+// updateGammaXi: draws in order k, d, p, m
+int ref_update_gamma_xi(int K, int P, int M, int D, double nu_gamma, const double* delta_xi, const double* xi,
+                        double* gamma_out) {
+  arma::field<arma::cube> xif(1, K), gx(1, K);
+  for (int k = 0; k < K; k++) {
+    xif(0, k) = cube_in(xi + (size_t)k * P * D * M, P, D, M);
+    gx(0, k) = arma::cube(P, D, M, arma::fill::ones);
+  }
+  arma::cube del = cube_in(delta_xi, K, M, D);
+  BayesFMMM::updateGammaXi(nu_gamma, del, xif, 0, 1, gx);
+  for (int k = 0; k < K; k++) cube_out(gx(0, k), gamma_out + (size_t)k * P * D * M);
+  return 0;
+}
+// updateAXi: per (j, i, d): 1 uniform (proposal) + 1 uniform
+int ref_update_A_xi(int K, int M, int D, double a1l, double b1l, double a2l, double b2l, const double* delta_xi,
+                    double ve1, double ve2, const double* A_in, double* A_out) {
+  arma::cube del = cube_in(delta_xi, K, M, D);
+  arma::field<arma::cube> a(1, 1);
+  a(0, 0) = cube_in(A_in, K, 2, D);
+  BayesFMMM::updateAXi(a1l, b1l, a2l, b2l, del, ve1, ve2, 0, 1, a);
+  cube_out(a(0, 0), A_out);
+  return 0;
+}
+
 }  // extern "C"
