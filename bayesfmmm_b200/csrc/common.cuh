@@ -15,7 +15,6 @@
 
 namespace bf {
 
-constexpr int VEC = 2;          // functions per thread in the per-function passes (16-byte loads)
 constexpr int DMAX = 4;         // covariates supported by the covariate-adjusted kernels
 constexpr int PF_THREADS = 128; // block size of the per-function passes
 constexpr int RED_MAX = 8;      // values reduced per block in the per-function passes (K+1 <= 8)
@@ -30,7 +29,7 @@ struct PassArgs {
   const double* __restrict__ glob;
   double sigma_sq, beta;
   // Z step
-  double alpha3, a_Z_PM;
+  double alpha3, a_Z_PM, log_a_Z_PM;
   double pi[8];
   const double* __restrict__ gam;   // injected draws [K][ld] or nullptr (device RNG)
   const double* __restrict__ u;     // [ld] or nullptr
@@ -70,14 +69,25 @@ struct Philox {
 // Stream of doubles for one (function, iteration, purpose): counter = (index lo, index hi,
 // iteration*64 + purpose, running block number).  Results depend only on the GLOBAL function
 // index, so a chain is independent of how functions are sharded over GPUs.
+// Out-of-line FP64 transcendental wrappers.  libdevice inlines ~50-1000 instructions per call of
+// log / lgamma / pow; with K- and V-unrolled callers that made the Z kernel 180 KB of SASS and the
+// instruction cache (not FP64 or HBM) its bound (profiles/: stall_no_inst).  One copy per kernel.
+#ifdef __CUDA_ARCH__
+#define BF_NOINLINE __noinline__
+#else
+#define BF_NOINLINE
+#endif
+__host__ __device__ BF_NOINLINE inline double nl_log(double x) { return log(x); }
+__host__ __device__ BF_NOINLINE inline double nl_lgamma(double x) { return lgamma(x); }
+__host__ __device__ BF_NOINLINE inline double nl_pow(double x, double y) { return pow(x, y); }
+
 struct RngStream {
   uint32_t c0, c1, c2, ctr, k0, k1;
   double spare; int have;
   __host__ __device__ RngStream(uint64_t key, uint64_t index, uint64_t iteration, uint32_t purpose)
       : c0((uint32_t)index), c1((uint32_t)(index >> 32)), c2((uint32_t)(iteration * 64 + purpose)), ctr(0),
         k0((uint32_t)key), k1((uint32_t)(key >> 32)), spare(0), have(0) {}
-  __host__ __device__ inline double uniform() {     // (0,1), 53 bits
-    if (have) { have = 0; return spare; }
+  __host__ __device__ BF_NOINLINE double refill() {   // one Philox block -> two 53-bit uniforms
     uint32_t c[4] = {c0, c1, c2, ctr++};
     Philox::block(c, k0, k1);
     uint64_t a = ((uint64_t)c[0] << 32) | c[1], b = ((uint64_t)c[2] << 32) | c[3];
@@ -85,7 +95,11 @@ struct RngStream {
     have = 1;
     return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   }
-  __host__ __device__ inline double normal() {      // Box-Muller, one value per two uniforms
+  __host__ __device__ inline double uniform() {     // (0,1), 53 bits
+    if (have) { have = 0; return spare; }
+    return refill();
+  }
+  __host__ __device__ BF_NOINLINE double normal() {      // Box-Muller, one value per two uniforms
     double u1 = uniform(), u2 = uniform();
     double r = sqrt(-2.0 * log(u1));
 #ifdef __CUDA_ARCH__
@@ -95,9 +109,9 @@ struct RngStream {
 #endif
   }
   // Marsaglia-Tsang; shape < 1 boosted by U^(1/shape)
-  __host__ __device__ inline double gamma(double shape) {
+  __host__ __device__ BF_NOINLINE double gamma(double shape) {
     double boost = 1.0;
-    if (shape < 1.0) { boost = pow(uniform(), 1.0 / shape); shape += 1.0; }
+    if (shape < 1.0) { boost = nl_pow(uniform(), 1.0 / shape); shape += 1.0; }
     double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
     for (int it = 0; it < 64; it++) {
       double x = normal();
@@ -107,7 +121,7 @@ struct RngStream {
       double uu = uniform();
       double x2 = x * x;
       if (uu < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
-      if (log(uu) < 0.5 * x2 + d * (1.0 - v + log(v))) return boost * d * v;
+      if (nl_log(uu) < 0.5 * x2 + d * (1.0 - v + nl_log(v))) return boost * d * v;
     }
     return boost * d;   // unreachable in practice (acceptance > 95% per trial)
   }
@@ -175,7 +189,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) 
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
-int pass_grid(int n);
+int pass_grid(int ld, int v);
 
 struct StatsArgs {
   int n, ld, P, K, M, D, q;

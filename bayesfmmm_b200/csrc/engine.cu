@@ -225,7 +225,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMalloc(&e->draws, ld * (std::max(e->K + 1, e->M)) * 8));
   e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q;
   CUE(cudaMalloc(&e->stats, e->stats_len * 8));
-  e->pass_blocks = bf::pass_grid(e->ld);
+  e->pass_blocks = bf::pass_grid(e->ld, 1);
   CUE(cudaMalloc(&e->partials, (size_t)e->pass_blocks * bf::RED_MAX * 8));
   e->st_blocks = bf::stats_blocks(e->sm_count);
   CUE(cudaMalloc(&e->st_partials, bf::stats_partial_doubles(e->P, e->q, e->st_blocks) * 8));
@@ -358,7 +358,7 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
                     bool dump_draws) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
-  a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM;
+  a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM);
   for (int k = 0; k < e->K; k++) a.pi[k] = pi[k];
   if (injected) { a.gam = e->draws; a.u = e->draws + (size_t)e->K * e->ld; }
   if (dump_draws) a.draws_out = e->draws;
@@ -558,5 +558,5 @@ int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
 }  // extern "C"
 
 namespace bf {
-int pass_grid(int ld) { return (ld + PF_THREADS * VEC - 1) / (PF_THREADS * VEC); }
+int pass_grid(int ld, int v) { return (ld + PF_THREADS * v - 1) / (PF_THREADS * v); }
 }

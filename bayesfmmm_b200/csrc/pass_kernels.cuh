@@ -1,5 +1,5 @@
 // pass_kernels.cuh -- the three per-function passes (Z Metropolis step, chi sweep, residual
-// sum of squares) over the projected coefficient cache.  One thread owns VEC = 2 adjacent
+// sum of squares) over the projected coefficient cache.  One thread owns V (1 or 2) adjacent
 // functions; every global access is a 16-byte load/store on coefficient-major (SoA) arrays, so a
 // warp reads 512 contiguous bytes per row.  The global coefficients live in shared memory
 // (broadcast reads).  K and M are compile-time so all per-function state stays in registers.
@@ -8,13 +8,82 @@
 
 namespace bf {
 
+// V functions per thread: V = 2 -> 16-byte accesses, V = 1 -> 8-byte accesses (half the registers,
+// twice the resident warps: used by the latency-bound kernels).
+template <int V> __device__ __forceinline__ void ldv(const double* p, double (&o)[V]) {
+  if constexpr (V == 2) { double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y; }
+  else o[0] = *p;
+}
+template <int V> __device__ __forceinline__ void ldv_cs(const double* p, double (&o)[V]) {
+  if constexpr (V == 2) { double2 t = __ldcs(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y; }
+  else o[0] = __ldcs(p);
+}
+template <int V> __device__ __forceinline__ void stv(double* p, const double (&o)[V]) {
+  if constexpr (V == 2) *reinterpret_cast<double2*>(p) = make_double2(o[0], o[1]);
+  else *p = o[0];
+}
+
+// Streams the P rows of the coefficient cache for the V functions of this thread with the loads of
+// the NEXT group of CH rows in flight while the current group is consumed (software pipelining:
+// without it the passes sit on long-scoreboard stalls, see profiles/).  Loads are ld.global.cs
+// (streamed once per pass, evict-first).
+template <int V, int CH, typename F>
+__device__ __forceinline__ void stream_rows(const double* __restrict__ base, int ld, int P, int i0, F&& body) {
+  double cur[CH][V], nxt[CH][V];
+  const double* col = base + i0;
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    if (j < P) ldv_cs<V>(col + (size_t)j * ld, cur[j]);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; v++) cur[j][v] = 0.0;
+    }
+  }
+  for (int p0 = 0; p0 < P; p0 += CH) {
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+      const int p = p0 + CH + j;
+      if (p < P) ldv_cs<V>(col + (size_t)p * ld, nxt[j]);
+      else {
+#pragma unroll
+        for (int v = 0; v < V; v++) nxt[j][v] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; j++)
+      if (p0 + j < P) body(p0 + j, cur[j]);
+#pragma unroll
+    for (int j = 0; j < CH; j++)
+#pragma unroll
+      for (int v = 0; v < V; v++) cur[j][v] = nxt[j][v];
+  }
+}
+constexpr int ROW_CH = 4;
+
+// log Gamma(x) for x > 0 when lx = log(x) is already known.  For x >= 16 Stirling's series
+//   (x - 1/2) log x - x + log(2 pi)/2 + 1/(12x) - 1/(360x^3) + 1/(1260x^5) - 1/(1680x^7) + 1/(1188x^9)
+// is exact to double rounding (next term 691/(360360 x^11) < 1e-16 at x = 16) and needs no further
+// transcendental; smaller arguments fall back to the library lgamma.  The Z step evaluates
+// 2(K+1) log-Gammas per function (calc_lB, Distributions.h:51-61).
+__device__ __forceinline__ double lgamma_known_log(double x, double lx) {
+  if (x >= 16.0) {
+    const double r = 1.0 / x, r2 = r * r;
+    double s = fma(r2, 8.417508417508417508e-4, -5.952380952380952381e-4);   //  1/1188, -1/1680
+    s = fma(r2, s, 7.936507936507936508e-4);                                  //  1/1260
+    s = fma(r2, s, -2.777777777777777778e-3);                                 // -1/360
+    s = fma(r2, s, 8.333333333333333333e-2);                                  //  1/12
+    return fma(x - 0.5, lx, -x) + fma(r, s, 0.918938533204672741780329736406);
+  }
+  return nl_lgamma(x);
+}
+
 // Effective coefficients of one function at basis column p:
 //   a[k][0]   = (nu_k + eta_k x_i)[p],   a[k][m+1] = (phi_km + xi_km x_i)[p]     (whitened)
-template <int K, int M, bool COV>
+template <int K, int M, bool COV, int V>
 struct Coef {
-  static constexpr int NV = COV ? VEC : 1;
+  static constexpr int NV = COV ? V : 1;
   double a[NV][K][M + 1];
-  __device__ __forceinline__ void load(const double* __restrict__ gs, int D, const double (&x)[VEC][DMAX]) {
+  __device__ __forceinline__ void load(const double* __restrict__ gs, int D, const double (&x)[V][DMAX]) {
     if constexpr (!COV) {
       constexpr int Q = K * (M + 1);
       double flat[Q + 1];
@@ -37,13 +106,13 @@ struct Coef {
           const double* b = gs + (k * (M + 1) + m) * stride;
           double base = b[0];
 #pragma unroll
-          for (int v = 0; v < VEC; v++) a[v][k][m] = base;
+          for (int v = 0; v < V; v++) a[v][k][m] = base;
 #pragma unroll
           for (int d = 0; d < DMAX; d++)
             if (d < D) {
               double g = b[1 + d];
 #pragma unroll
-              for (int v = 0; v < VEC; v++) a[v][k][m] = fma(x[v][d], g, a[v][k][m]);
+              for (int v = 0; v < V; v++) a[v][k][m] = fma(x[v][d], g, a[v][k][m]);
             }
         }
     }
@@ -51,20 +120,35 @@ struct Coef {
   __device__ __forceinline__ double get(int v, int k, int m) const { return a[COV ? v : 0][k][m]; }
 };
 
-template <int K, int M, bool COV>
+template <int K, int M, bool COV, int V>
 struct FnState {
-  double z[VEC][K], chi[VEC][M > 0 ? M : 1], x[VEC][DMAX];
+  double z[V][K], chi[V][M > 0 ? M : 1], x[V][DMAX];
   __device__ __forceinline__ void load(const PassArgs& a, int i0) {
+    double t[V];
 #pragma unroll
-    for (int k = 0; k < K; k++) { double2 t = ld2(a.Z + (size_t)k * a.ld + i0); z[0][k] = t.x; z[1][k] = t.y; }
+    for (int k = 0; k < K; k++) {
+      ldv<V>(a.Z + (size_t)k * a.ld + i0, t);
 #pragma unroll
-    for (int m = 0; m < M; m++) { double2 t = ld2(a.chi + (size_t)m * a.ld + i0); chi[0][m] = t.x; chi[1][m] = t.y; }
+      for (int v = 0; v < V; v++) z[v][k] = t[v];
+    }
 #pragma unroll
-    for (int d = 0; d < DMAX; d++) { x[0][d] = 0; x[1][d] = 0; }
+    for (int m = 0; m < M; m++) {
+      ldv<V>(a.chi + (size_t)m * a.ld + i0, t);
+#pragma unroll
+      for (int v = 0; v < V; v++) chi[v][m] = t[v];
+    }
+#pragma unroll
+    for (int d = 0; d < DMAX; d++)
+#pragma unroll
+      for (int v = 0; v < V; v++) x[v][d] = 0;
     if constexpr (COV) {
 #pragma unroll
       for (int d = 0; d < DMAX; d++)
-        if (d < a.D) { double2 t = ld2(a.X + (size_t)d * a.ld + i0); x[0][d] = t.x; x[1][d] = t.y; }
+        if (d < a.D) {
+          ldv<V>(a.X + (size_t)d * a.ld + i0, t);
+#pragma unroll
+          for (int v = 0; v < V; v++) x[v][d] = t[v];
+        }
     }
   }
 };
@@ -80,27 +164,31 @@ __device__ __forceinline__ void stage_globals(const PassArgs& a, double* g) {
 // Z_proposal_density :102-113; rdirichlet Distributions.h:22-45; calc_lB :51-61).
 // The squared-error terms are evaluated in the whitened coefficient space, where
 // ||y - B theta||^2 = rss_i + ||c~_i - theta~||^2 and rss_i cancels in the ratio.
-template <int K, int M, bool COV>
-__global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
+template <int K, int M, bool COV, int V>
+__global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
-  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * VEC;
+  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
   double red[K + 1];
 #pragma unroll
   for (int j = 0; j <= K; j++) red[j] = 0;
   if (i0 < a.ld) {
-    FnState<K, M, COV> st;
+    FnState<K, M, COV, V> st;
     st.load(a, i0);
-    double zp[VEC][K], uacc[VEC];
+    double zp[V][K], uacc[V];
     // ---- proposal
     if (a.gam) {
+      double t[V];
 #pragma unroll
-      for (int k = 0; k < K; k++) { double2 t = ld2_stream(a.gam + (size_t)k * a.ld + i0); zp[0][k] = t.x; zp[1][k] = t.y; }
-      double2 t = ld2_stream(a.u + i0);
-      uacc[0] = t.x; uacc[1] = t.y;
+      for (int k = 0; k < K; k++) {
+        ldv_cs<V>(a.gam + (size_t)k * a.ld + i0, t);
+#pragma unroll
+        for (int v = 0; v < V; v++) zp[v][k] = t[v];
+      }
+      ldv_cs<V>(a.u + i0, uacc);
     } else {
 #pragma unroll
-      for (int v = 0; v < VEC; v++) {
+      for (int v = 0; v < V; v++) {
         RngStream rs(a.key, a.global_offset + (uint64_t)(i0 + v), a.iteration, RNG_Z_PROPOSAL);
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -111,13 +199,18 @@ __global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
         uacc[v] = rs.uniform();
       }
       if (a.draws_out) {
+        double t[V];
 #pragma unroll
-        for (int k = 0; k < K; k++) st2(a.draws_out + (size_t)k * a.ld + i0, zp[0][k], zp[1][k]);
-        st2(a.draws_out + (size_t)K * a.ld + i0, uacc[0], uacc[1]);
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+          for (int v = 0; v < V; v++) t[v] = zp[v][k];
+          stv<V>(a.draws_out + (size_t)k * a.ld + i0, t);
+        }
+        stv<V>(a.draws_out + (size_t)K * a.ld + i0, uacc);
       }
     }
 #pragma unroll
-    for (int v = 0; v < VEC; v++) {
+    for (int v = 0; v < V; v++) {
       double sum = 0;
 #pragma unroll
       for (int k = 0; k < K; k++) sum += zp[v][k];
@@ -125,15 +218,14 @@ __global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
       for (int k = 0; k < K; k++) zp[v][k] = zp[v][k] / sum;
     }
     // ---- squared errors of the current and the proposed state
-    double so[VEC] = {0, 0}, sn[VEC] = {0, 0};
-    Coef<K, M, COV> cf;
-#pragma unroll 4
-    for (int p = 0; p < a.P; p++) {
-      double2 c2 = ld2_stream(a.Ct + (size_t)p * a.ld + i0);
-      const double c[VEC] = {c2.x, c2.y};
+    double so[V], sn[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { so[v] = 0; sn[v] = 0; }
+    Coef<K, M, COV, V> cf;
+    stream_rows<V, ROW_CH>(a.Ct, a.ld, a.P, i0, [&](int p, const double (&c)[V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
-      for (int v = 0; v < VEC; v++) {
+      for (int v = 0; v < V; v++) {
         double ro = c[v], rn = c[v];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -146,18 +238,18 @@ __global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
         so[v] = fma(ro, ro, so[v]);
         sn[v] = fma(rn, rn, sn[v]);
       }
-    }
+    });
     // ---- acceptance
-    double znew[VEC][K];
+    double znew[V][K];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) {
+    for (int v = 0; v < V; v++) {
       double lzo[K], lzn[K];
       double lp_old = 0, lp_new = 0;
       bool nonpos = false;
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        lzo[k] = log(st.z[v][k]);
-        lzn[k] = log(zp[v][k]);
+        lzo[k] = nl_log(st.z[v][k]);
+        lzn[k] = nl_log(zp[v][k]);
         lp_old += (a.alpha3 * a.pi[k] - 1) * lzo[k];
         lp_new += (a.alpha3 * a.pi[k] - 1) * lzn[k];
         nonpos |= (st.z[v][k] <= 0);
@@ -171,15 +263,16 @@ __global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
         double al_from_new = a.a_Z_PM * zp[v][k];     // parameters of the reverse move
         q_new += (al_from_old - 1) * lzn[k];
         q_old += (al_from_new - 1) * lzo[k];
-        lB_new += lgamma(al_from_old); tot_new += al_from_old;
-        lB_old += lgamma(al_from_new); tot_old += al_from_new;
+        // log(a * z) = log a + log z: both logs are already in registers
+        lB_new += lgamma_known_log(al_from_old, a.log_a_Z_PM + lzo[k]); tot_new += al_from_old;
+        lB_old += lgamma_known_log(al_from_new, a.log_a_Z_PM + lzn[k]); tot_old += al_from_new;
       }
-      q_new -= (lB_new - lgamma(tot_new));
-      q_old -= (lB_old - lgamma(tot_old));
+      q_new -= (lB_new - lgamma_known_log(tot_new, nl_log(tot_new)));
+      q_old -= (lB_old - lgamma_known_log(tot_old, nl_log(tot_old)));
       double acc = lp_new - lp_old + q_old - q_new;
       if (nonpos) acc = 1;                           // UpdateMixedMembership.h:170-174
       const bool live = (i0 + v) < a.n;
-      const bool take = live && (log(uacc[v]) < acc);
+      const bool take = live && (nl_log(uacc[v]) < acc);
       if (a.acc_out && live) a.acc_out[i0 + v] = acc;
 #pragma unroll
       for (int k = 0; k < K; k++) {
@@ -188,8 +281,15 @@ __global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
       }
       if (take) red[K] += 1.0;
     }
+    {
+      double t[V];
 #pragma unroll
-    for (int k = 0; k < K; k++) st2(a.Z + (size_t)k * a.ld + i0, znew[0][k], znew[1][k]);
+      for (int k = 0; k < K; k++) {
+#pragma unroll
+        for (int v = 0; v < V; v++) t[v] = znew[v][k];
+        stv<V>(a.Z + (size_t)k * a.ld + i0, t);
+      }
+    }
   }
   grid_reduce<K + 1>(red, a);
 }
@@ -199,32 +299,31 @@ __global__ void __launch_bounds__(PF_THREADS) z_kernel(const PassArgs a) {
 // Gram G[m][n] = ph_m . ph_n and r[m] = ph_m . (y - B mu) are accumulated once (in coefficient
 // space), then the reference's sequential m = 0..M-1 sweep is run on them, so chi(i,n) for n < m
 // is the already-updated value exactly as in UpdateChi.h:48.
-template <int K, int M, bool COV>
-__global__ void __launch_bounds__(PF_THREADS) chi_kernel(const PassArgs a) {
+template <int K, int M, bool COV, int V>
+__global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
-  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * VEC;
+  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
   double red[1] = {0};
   if (i0 < a.ld) {
-    FnState<K, M, COV> st;
+    FnState<K, M, COV, V> st;
     st.load(a, i0);
-    double G[VEC][M][M], r[VEC][M], d0[VEC] = {0, 0};
+    double G[V][M][M], r[V][M], d0[V];
 #pragma unroll
-    for (int v = 0; v < VEC; v++)
+    for (int v = 0; v < V; v++) {
+      d0[v] = 0;
 #pragma unroll
       for (int m = 0; m < M; m++) {
         r[v][m] = 0;
 #pragma unroll
         for (int q = 0; q < M; q++) G[v][m][q] = 0;
       }
-    Coef<K, M, COV> cf;
-#pragma unroll 4
-    for (int p = 0; p < a.P; p++) {
-      double2 c2 = ld2_stream(a.Ct + (size_t)p * a.ld + i0);
-      const double c[VEC] = {c2.x, c2.y};
+    }
+    Coef<K, M, COV, V> cf;
+    stream_rows<V, ROW_CH>(a.Ct, a.ld, a.P, i0, [&](int p, const double (&c)[V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
-      for (int v = 0; v < VEC; v++) {
+      for (int v = 0; v < V; v++) {
         double dres = c[v], um[M];
 #pragma unroll
         for (int m = 0; m < M; m++) um[m] = 0;
@@ -242,27 +341,37 @@ __global__ void __launch_bounds__(PF_THREADS) chi_kernel(const PassArgs a) {
           for (int q = m; q < M; q++) G[v][m][q] = fma(um[m], um[q], G[v][m][q]);
         }
       }
-    }
-    double eps[VEC][M];
+    });
+    double eps[V][M];
     if (a.eps) {
+      double t[V];
 #pragma unroll
-      for (int m = 0; m < M; m++) { double2 t = ld2_stream(a.eps + (size_t)m * a.ld + i0); eps[0][m] = t.x; eps[1][m] = t.y; }
+      for (int m = 0; m < M; m++) {
+        ldv_cs<V>(a.eps + (size_t)m * a.ld + i0, t);
+#pragma unroll
+        for (int v = 0; v < V; v++) eps[v][m] = t[v];
+      }
     } else {
 #pragma unroll
-      for (int v = 0; v < VEC; v++) {
+      for (int v = 0; v < V; v++) {
         RngStream rs(a.key, a.global_offset + (uint64_t)(i0 + v), a.iteration, RNG_CHI);
 #pragma unroll
         for (int m = 0; m < M; m++) eps[v][m] = rs.normal();
       }
       if (a.draws_out) {
+        double t[V];
 #pragma unroll
-        for (int m = 0; m < M; m++) st2(a.draws_out + (size_t)m * a.ld + i0, eps[0][m], eps[1][m]);
+        for (int m = 0; m < M; m++) {
+#pragma unroll
+          for (int v = 0; v < V; v++) t[v] = eps[v][m];
+          stv<V>(a.draws_out + (size_t)m * a.ld + i0, t);
+        }
       }
     }
-    const double2 rs2 = ld2(a.rss + i0);
-    const double rssv[VEC] = {rs2.x, rs2.y};
+    double rssv[V];
+    ldv<V>(a.rss + i0, rssv);
 #pragma unroll
-    for (int v = 0; v < VEC; v++) {
+    for (int v = 0; v < V; v++) {
 #pragma unroll
       for (int m = 0; m < M; m++) {
         double w = r[v][m];
@@ -285,32 +394,38 @@ __global__ void __launch_bounds__(PF_THREADS) chi_kernel(const PassArgs a) {
       }
       if (i0 + v < a.n) red[0] += rssv[v] + (d0[v] - 2 * lin + quad);
     }
+    {
+      double t[V];
 #pragma unroll
-    for (int m = 0; m < M; m++) st2(a.chi + (size_t)m * a.ld + i0, st.chi[0][m], st.chi[1][m]);
+      for (int m = 0; m < M; m++) {
+#pragma unroll
+        for (int v = 0; v < V; v++) t[v] = st.chi[v][m];
+        stv<V>(a.chi + (size_t)m * a.ld + i0, t);
+      }
+    }
   }
   grid_reduce<1>(red, a);
 }
 
 // ================================================================= residual sum of squares
 // the data pass of updateSigma / calcLikelihood (UpdateSigma.h:36-50, CalculateLikelihood.h:28-42)
-template <int K, int M, bool COV>
+template <int K, int M, bool COV, int V>
 __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
-  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * VEC;
+  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
   double red[1] = {0};
   if (i0 < a.ld) {
-    FnState<K, M, COV> st;
+    FnState<K, M, COV, V> st;
     st.load(a, i0);
-    double acc[VEC] = {0, 0};
-    Coef<K, M, COV> cf;
-#pragma unroll 4
-    for (int p = 0; p < a.P; p++) {
-      double2 c2 = ld2_stream(a.Ct + (size_t)p * a.ld + i0);
-      const double c[VEC] = {c2.x, c2.y};
+    double acc[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) acc[v] = 0;
+    Coef<K, M, COV, V> cf;
+    stream_rows<V, ROW_CH>(a.Ct, a.ld, a.P, i0, [&](int p, const double (&c)[V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
-      for (int v = 0; v < VEC; v++) {
+      for (int v = 0; v < V; v++) {
         double res = c[v];
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -321,10 +436,12 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
         }
         acc[v] = fma(res, res, acc[v]);
       }
-    }
-    const double2 rs2 = ld2(a.rss + i0);
-    if (i0 < a.n) red[0] += rs2.x + acc[0];
-    if (i0 + 1 < a.n) red[0] += rs2.y + acc[1];
+    });
+    double rssv[V];
+    ldv<V>(a.rss + i0, rssv);
+#pragma unroll
+    for (int v = 0; v < V; v++)
+      if (i0 + v < a.n) red[0] += rssv[v] + acc[v];
   }
   grid_reduce<1>(red, a);
 }
@@ -339,14 +456,14 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
   X(6, 1) X(6, 2) X(6, 3) X(6, 4) X(6, 5) X(6, 6)
 #endif
 
-template <typename Kern>
+template <int V, typename Kern>
 inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s) {
   size_t smem = (size_t)a.P * a.QS * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<pass_grid(a.ld), PF_THREADS, smem, s>>>(a);
+  kern<<<pass_grid(a.ld, V), PF_THREADS, smem, s>>>(a);
   g_launch_count++;
   return (int)cudaGetLastError();
 }

@@ -75,27 +75,39 @@ __global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
 
   const int n_chunks = a.ld >> 3;
   const int wstride = gridDim.x * ST_WARPS;
-  for (int ch = blockIdx.x * ST_WARPS + warp; ch < n_chunks; ch += wstride) {
-    const int i = (ch << 3) + 2 * c;
-    double2 av[MT], wv[NT];
+  // operands of one 8-function chunk; two chunks are kept in flight ahead of the one being multiplied
+  struct Ops { double2 av[MT], z[NT], ch[NT], x[NT]; };
+  auto fetch = [&](Ops& o, int chunk) {
+    const bool ok = chunk < n_chunks;
+    const int i = (chunk << 3) + 2 * c;
 #pragma unroll
-    for (int mt = 0; mt < MT; mt++) av[mt] = ap[mt] ? ld2_stream(ap[mt] + i) : make_double2(0.0, 0.0);
+    for (int mt = 0; mt < MT; mt++)
+      o.av[mt] = (ok && ap[mt]) ? __ldcs(reinterpret_cast<const double2*>(ap[mt] + i)) : make_double2(0.0, 0.0);
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
-      double2 w = make_double2(0.0, 0.0);
-      if (zp[nt]) {
-        w = ld2(zp[nt] + i);
-        if (cp[nt]) { double2 t = ld2(cp[nt] + i); w.x *= t.x; w.y *= t.y; }
-        if (xp[nt]) { double2 t = ld2(xp[nt] + i); w.x *= t.x; w.y *= t.y; }
-      }
-      wv[nt] = w;
+      o.z[nt] = (ok && zp[nt]) ? ld2(zp[nt] + i) : make_double2(0.0, 0.0);
+      o.ch[nt] = (ok && cp[nt]) ? ld2(cp[nt] + i) : make_double2(1.0, 1.0);
+      o.x[nt] = (ok && xp[nt]) ? ld2(xp[nt] + i) : make_double2(1.0, 1.0);
+    }
+  };
+  Ops o0, o1, o2;
+  int ch = blockIdx.x * ST_WARPS + warp;
+  fetch(o0, ch);
+  fetch(o1, ch + wstride);
+  for (; ch < n_chunks; ch += wstride) {
+    fetch(o2, ch + 2 * wstride);
+    double2 wv[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      wv[nt].x = o0.z[nt].x * o0.ch[nt].x * o0.x[nt].x;
+      wv[nt].y = o0.z[nt].y * o0.ch[nt].y * o0.x[nt].y;
     }
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        dmma884(R[mt][nt][0], R[mt][nt][1], av[mt].x, wv[nt].x);
-        dmma884(R[mt][nt][0], R[mt][nt][1], av[mt].y, wv[nt].y);
+        dmma884(R[mt][nt][0], R[mt][nt][1], o0.av[mt].x, wv[nt].x);
+        dmma884(R[mt][nt][0], R[mt][nt][1], o0.av[mt].y, wv[nt].y);
       }
     if (do_wtw) {
 #pragma unroll
@@ -106,6 +118,7 @@ __global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
           dmma884(S[n1][n2][0], S[n1][n2][1], wv[n1].y, wv[n2].y);
         }
     }
+    o0 = o1; o1 = o2;
   }
 
   // block reduction: warps add their fragments into shared memory one after the other (fixed order)
@@ -135,11 +148,13 @@ __global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
   for (int idx = threadIdx.x; idx < TILES * 64; idx += ST_THREADS) row[idx] = s_acc[idx];
 }
 
-// second stage: one thread per output element sums the block partials in block order
+// second stage: one warp per output element sums the block partials (lane-strided, then a shuffle
+// tree: a fixed order for a fixed grid, so the result is reproducible)
 template <int MT, int NT>
-__global__ void stats_final_kernel(const StatsArgs a, int gx) {
+__global__ void __launch_bounds__(256) stats_final_kernel(const StatsArgs a, int gx) {
   constexpr int TILES = MT * NT + NT * NT;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   const int nR = a.P * a.q, nS = a.q * a.q;
   if (e >= nR + nS) return;
   int by, idx;
@@ -157,11 +172,12 @@ __global__ void stats_final_kernel(const StatsArgs a, int gx) {
   }
   const double* base = a.partials + (size_t)by * gx * (TILES * 64) + idx;
   double t = 0;
-  for (int b = 0; b < gx; b++) t += base[(size_t)b * (TILES * 64)];
-  if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t;
+  for (int b = lane; b < gx; b += 32) t += base[(size_t)b * (TILES * 64)];
+  t = warp_sum(t);
+  if (lane == 0) { if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t; }
 }
 
-int stats_blocks(int sm_count) { return sm_count * 4; }
+int stats_blocks(int sm_count) { return sm_count; }
 
 static inline void stats_shape(int P, int q, int& MT, int& NT, int& gy) {
   NT = (q + 7) / 8;
@@ -182,7 +198,7 @@ static int launch_stats_t(const StatsArgs& a, int gy, cudaStream_t s) {
   dim3 grid(a.blocks, gy);
   stats_kernel<MT, NT><<<grid, ST_THREADS, 0, s>>>(a);
   int tot = a.P * a.q + a.q * a.q;
-  stats_final_kernel<MT, NT><<<(tot + 127) / 128, 128, 0, s>>>(a, a.blocks);
+  stats_final_kernel<MT, NT><<<(tot + 7) / 8, 256, 0, s>>>(a, a.blocks);
   g_launch_count += 2;
   return (int)cudaGetLastError();
 }

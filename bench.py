@@ -282,7 +282,7 @@ def run_ours(a):
     g = smp.get()
     pi_now, a3 = g["pi"], g["alpha3"]
     kern = {
-        "z_kernel": (kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM)), n * (P + 3 * K + M) * 8),
+        "z_kernel": (kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM)), n * (P + 2 * K + M) * 8),
         "chi_kernel": (kernel_ms(lambda: eng.update_chi_async()), n * (P + 1 + K + 2 * M) * 8),
         "ssr_kernel": (kernel_ms(lambda: eng.ssr_async()), n * (P + 1 + K + M) * 8),
         "stats_kernel": (kernel_ms(lambda: eng.suffstats_async()), n * (P + K + M) * 8),
