@@ -38,6 +38,7 @@ struct bfmmm_engine {
   int sm_count = 148;
   // device
   double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
+  double *snapZ = nullptr, *snapChi = nullptr;   // device copy of (Z, chi) for tempered transitions
   double *draws = nullptr, *stats = nullptr, *partials = nullptr, *st_partials = nullptr, *acc_dbg = nullptr;
   unsigned int* ticket = nullptr;
   int64_t stats_len = 0;
@@ -83,7 +84,7 @@ void free_all(bfmmm_engine* e) {
   cudaSetDevice(e->device);
   cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
   cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
-  cudaFree(e->acc_dbg);
+  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi);
   for (int i = 0; i < N_STAGE; i++) {
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
@@ -468,6 +469,25 @@ int bfmmm_suffstats(bfmmm_engine* e, double* WtW, double* BtYW) {
   CU(cudaStreamSynchronize(e->stream));
   if (WtW) std::copy(e->h_stats + e->off_wtw(), e->h_stats + e->off_ctw(), WtW);
   if (BtYW) unwhiten(e, e->h_stats + e->off_ctw(), BtYW);
+  return 0;
+}
+
+// device-side copy of the per-function state, so a rejected tempered transition
+// (BFMMM.h:1631-1651 keeps the pre-transition slice) can be undone without a host round trip
+int bfmmm_state_snapshot(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (!e->snapZ) CU(cudaMalloc(&e->snapZ, (size_t)e->ld * e->K * 8));
+  if (!e->snapChi) CU(cudaMalloc(&e->snapChi, (size_t)e->ld * e->M * 8));
+  CU(cudaMemcpyAsync(e->snapZ, e->Z, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->snapChi, e->chi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+int bfmmm_state_restore(bfmmm_engine* e) {
+  if (!e || !e->snapZ) return fail("bfmmm_state_restore: no snapshot");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpyAsync(e->Z, e->snapZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->chi, e->snapChi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
 

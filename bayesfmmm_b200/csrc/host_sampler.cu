@@ -19,7 +19,7 @@ namespace {
 // ------------------------------------------------------------------ host random numbers
 // purposes of the global Philox streams (one stream per purpose and iteration)
 enum { HP_PI = 101, HP_ALPHA3, HP_PHI, HP_DELTA, HP_A, HP_GAMMA, HP_NU, HP_TAU, HP_SIGMA, HP_ETA, HP_XI,
-       HP_TAU_ETA, HP_DELTA_XI, HP_A_XI, HP_GAMMA_XI };
+       HP_TAU_ETA, HP_DELTA_XI, HP_A_XI, HP_GAMMA_XI, HP_TT };
 
 struct HostRng {
   uint64_t key = 0, iteration = 0;
@@ -168,6 +168,8 @@ struct bfmmm_sampler {
   int n = 0, K = 0, P = 0, M = 0, D = 0, q = 0;
   bool identity = false;
   int64_t n_total = 0, iteration = 0, last_accept = 0;
+  int64_t tick = 0;        // monotone counter keying every random stream (tempered steps advance it too)
+  bool in_tt = false;      // inside a tempered transition: sweeps do not advance `iteration`
   double sum_half_total = 0, n_points_total = 0;   // sum_i floor(n_i/2) and sum_i n_i over ALL shards
   HostRng rng;
   bfmmm_allreduce_fn allreduce = nullptr;
@@ -176,6 +178,9 @@ struct bfmmm_sampler {
   vecd nu, Phi, pi, delta, gamma, A, tau, eta, xi, tau_eta, delta_xi, gamma_xi, A_xi, Pmat, G;
   double sigma_sq = 1.0, alpha3 = 1.0, loglik = 0.0;
   vecd stats;     // host copy of the engine statistics buffer
+  vecd tt_ssr, tt_sigma;   // per-slot trace of the last tempered transition
+  double last_ssr = 0;     // SSR of the state the last sweep ended with
+  int64_t tt_accepts = 0, tt_total = 0;
   vecd work, Prec, C, Lc, rhs, v1, v2;
 
   double& nu_(int k, int p) { return nu[(size_t)p * K + k]; }
@@ -727,13 +732,13 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   if (!s) return sfail("null sampler");
   if (!s->e) return sfail("bfmmm_sampler_step: detached sampler has no engine");
   bfmmm_engine* e = s->e;
-  s->rng.iteration = (uint64_t)s->iteration;
+  s->rng.iteration = (uint64_t)s->tick;
   const bool do_z = (sweep == BFMMM_SWEEP_NU_Z || sweep == BFMMM_SWEEP_FULL);
   const bool do_phi = (sweep == BFMMM_SWEEP_THETA || sweep == BFMMM_SWEEP_FULL);
   const bool do_nu = do_z;
   const bool do_chi = do_phi;
   const bool tempered = beta != 1.0;
-  if (bfmmm_seed(e, s->rng.key, (uint64_t)s->iteration)) return 1;
+  if (bfmmm_seed(e, s->rng.key, (uint64_t)s->tick)) return 1;
   if (push_globals(s)) return 1;
   if (do_z) {                                              // updateZ_PM -> updatePi_PM -> updateAlpha3
     if (bfmmm_update_z_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, beta)) return 1;
@@ -784,14 +789,96 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
     ssr_ll = st_ssr(s);
   }
   // calcLikelihood (CalculateLikelihood.h:19-44; MV :137-159 with floor(P/2))
+  s->last_ssr = ssr_ll;
   if (s->identity)
     s->loglik = -((double)s->n_total * (double)(s->P / 2)) * std::log(2 * 3.14159265358979323846 * s->sigma_sq) -
                 ssr_ll / (2 * s->sigma_sq);
   else
     s->loglik = -s->n_points_total * (0.918938533204672741780329736406 + 0.5 * std::log(s->sigma_sq)) -
                 ssr_ll / (2 * s->sigma_sq);
-  s->iteration++;
+  s->tick++;
+  if (!s->in_tt) s->iteration++;
   return 0;
+}
+
+// One tempered transition (BFMMM.h:1556-1651; ladder :1452-1460; acceptance
+// CalculateTTAcceptance.h:22-97): 2 N_t tempered full sweeps up and down the ladder, then
+//   log A = sum_i (beta_{i+1} - beta_i) [ g(s_i) - g(s_{m-i}) ],  g(s) = -(N/2) log sigma_s^2 - SSR_s / (2 sigma_s^2),
+// accept iff log u < log A, otherwise every parameter (and Z, chi on the device) is restored.
+int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t, double* logA_out, int* accepted) {
+  if (!s || !s->e) return sfail("null sampler");
+  if (N_t < 1) return sfail("bfmmm_sampler_tempered_transition: N_t must be >= 1");
+  std::vector<double> ladder(N_t, 1.0);
+  ladder[N_t - 1] = beta_N_t;
+  const double geom = std::pow(beta_N_t, 1.0 / N_t);
+  for (int i = 1; i < N_t; i++) ladder[i] = ladder[i - 1] * geom;      // as written at BFMMM.h:1453-1460
+  const int m = 2 * N_t;
+  // slot 0: the current state.  Its SSR: one data pass with the current globals.
+  if (push_globals(s)) return 1;
+  if (bfmmm_ssr_async(s->e)) return 1;
+  if (reduce_and_read(s)) return 1;
+  s->tt_ssr.assign(m + 1, 0.0); s->tt_sigma.assign(m + 1, 0.0);
+  s->tt_ssr[0] = st_ssr(s); s->tt_sigma[0] = s->sigma_sq;
+  bfmmm_sampler saved = *s;                       // host-side copy of every global
+  if (bfmmm_state_snapshot(s->e)) return 1;
+  int temp_ind = 0;
+  s->in_tt = true;
+  for (int l = 1; l <= m; l++) {
+    if (bfmmm_sampler_step(s, BFMMM_SWEEP_FULL, ladder[temp_ind])) { s->in_tt = false; return 1; }
+    s->tt_ssr[l] = s->last_ssr; s->tt_sigma[l] = s->sigma_sq;
+    if (l < N_t) temp_ind++;
+    if (l > N_t) temp_ind--;
+  }
+  s->in_tt = false;
+  double logA = 0;
+  auto g = [&](double beta, int slot) {
+    return -(beta / 2) * s->n_points_total * std::log(s->tt_sigma[slot]) - (beta / (2 * s->tt_sigma[slot])) * s->tt_ssr[slot];
+  };
+  for (int i = 0; i + 1 < N_t; i++) {
+    logA += g(ladder[i + 1], i) - g(ladder[i], i);
+    logA += -g(ladder[i + 1], m - i) + g(ladder[i], m - i);
+  }
+  s->rng.iteration = (uint64_t)s->tick;
+  s->rng.open(HP_TT);
+  s->tick++;
+  const double logu = std::log(s->rng.uniform());
+  const bool ok = logu < logA;
+  s->tt_total++;
+  if (ok) s->tt_accepts++;
+  else {
+    // restore the pre-transition state but keep the bookkeeping that must advance
+    vecd tssr = s->tt_ssr, tsig = s->tt_sigma;
+    int64_t tk = s->tick, acc = s->tt_accepts, tot = s->tt_total;
+    HostRng rng = s->rng;
+    *s = saved;
+    s->tt_ssr = tssr; s->tt_sigma = tsig; s->tick = tk; s->tt_accepts = acc; s->tt_total = tot; s->rng = rng;
+    if (bfmmm_state_restore(s->e)) return 1;
+  }
+  s->iteration++;                                  // a transition is one outer iteration (BFMMM.h:1500)
+  if (logA_out) *logA_out = logA;
+  if (accepted) *accepted = ok ? 1 : 0;
+  return 0;
+}
+
+// BFMMM_MTT_warm_start's iteration schedule (BFMMM.h:1500-1556): a plain sweep unless i is a positive
+// multiple of n_temp_trans, in which case the sweep is replaced by a tempered transition.
+int bfmmm_sampler_run_mtt(bfmmm_sampler* s, int n_iter, int n_temp_trans, int N_t, double beta_N_t) {
+  if (!s) return sfail("null sampler");
+  if (n_temp_trans <= 0) n_temp_trans = n_iter + 1;          // UserFunctions.cpp:1353-1359
+  for (int it = 0; it < n_iter; it++) {
+    const int64_t i = s->iteration;
+    if ((i % n_temp_trans) != 0 || i == 0) {
+      if (bfmmm_sampler_step(s, BFMMM_SWEEP_FULL, 1.0)) return 1;
+    } else {
+      if (bfmmm_sampler_tempered_transition(s, N_t, beta_N_t, nullptr, nullptr)) return 1;
+    }
+  }
+  return 0;
+}
+int bfmmm_sampler_tt_trace(bfmmm_sampler* s, double* ssr, double* sigma, int n) {
+  if (!s) return sfail("null sampler");
+  for (int i = 0; i < n && i < (int)s->tt_ssr.size(); i++) { ssr[i] = s->tt_ssr[i]; sigma[i] = s->tt_sigma[i]; }
+  return (int)s->tt_ssr.size() == 0 ? sfail("no tempered transition has run") : 0;
 }
 
 int bfmmm_sampler_run(bfmmm_sampler* s, int sweep, int n_iter) {

@@ -133,6 +133,22 @@ class Sampler:
     def run(self, sweep, n_iter):
         self._chk(self._lib.bfmmm_sampler_run(self._h, int(sweep), int(n_iter)))
 
+    def tempered_transition(self, N_t, beta_N_t):
+        logA, acc = C.c_double(), C.c_int()
+        self._chk(self._lib.bfmmm_sampler_tempered_transition(self._h, int(N_t), C.c_double(beta_N_t),
+                                                              C.byref(logA), C.byref(acc)))
+        return logA.value, bool(acc.value)
+
+    def run_mtt(self, n_iter, n_temp_trans, N_t, beta_N_t):
+        self._chk(self._lib.bfmmm_sampler_run_mtt(self._h, int(n_iter), int(n_temp_trans), int(N_t),
+                                                  C.c_double(beta_N_t)))
+
+    def tt_trace(self, N_t):
+        n = 2 * N_t + 1
+        ssr, sig = np.zeros(n), np.zeros(n)
+        self._chk(self._lib.bfmmm_sampler_tt_trace(self._h, _p(ssr), _p(sig), n))
+        return ssr, sig
+
     @property
     def iteration(self):
         self._lib.bfmmm_sampler_iteration.restype = C.c_int64

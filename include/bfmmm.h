@@ -74,6 +74,11 @@ int bfmmm_get_basis(bfmmm_engine* e, double* B_out);
 int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi);
 int bfmmm_get_state(bfmmm_engine* e, double* Z, double* chi);     /* either may be NULL */
 
+/* device-side snapshot / restore of (Z, chi): a rejected tempered transition keeps the
+ * pre-transition slice (BFMMM.h:1631-1651) */
+int bfmmm_state_snapshot(bfmmm_engine* e);
+int bfmmm_state_restore(bfmmm_engine* e);
+
 /* ---- global parameters: pushed before the phases that read them ----------------------------- */
 /* eta/xi may be NULL when D == 0; Phi may be NULL when M == 0. */
 int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, const double* eta,

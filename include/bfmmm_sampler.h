@@ -77,6 +77,16 @@ int bfmmm_sampler_get_cov(bfmmm_sampler* s, double* eta, double* xi, double* tau
 int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta);
 /* n sweeps back to back (the loop bench.py times) */
 int bfmmm_sampler_run(bfmmm_sampler* s, int sweep, int n_iter);
+/* One tempered transition of BFMMM_MTT_warm_start (BFMMM.h:1556-1651, acceptance
+ * CalculateTTAcceptance.h:22-97): 2*N_t tempered sweeps over the geometric ladder
+ * (BFMMM.h:1452-1460), accepted with probability min(1, exp(logA)); on rejection every global and
+ * the device-resident Z, chi are restored. */
+int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t, double* logA, int* accepted);
+/* n iterations with the reference's schedule: a tempered transition replaces the sweep whenever
+ * the iteration index is a positive multiple of n_temp_trans (0 = never, UserFunctions.cpp:1353-1359) */
+int bfmmm_sampler_run_mtt(bfmmm_sampler* s, int n_iter, int n_temp_trans, int N_t, double beta_N_t);
+/* per-slot (SSR, sigma^2) of the last tempered transition, slots 0..2*N_t */
+int bfmmm_sampler_tt_trace(bfmmm_sampler* s, double* ssr, double* sigma, int n);
 int64_t bfmmm_sampler_iteration(bfmmm_sampler* s);
 /* acceptance count of the last Z step (summed over shards) */
 int64_t bfmmm_sampler_last_accept(bfmmm_sampler* s);
