@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/bfmmm_io.h"
 #include "../../include/bfmmm_sampler.h"
 #include "common.cuh"
 
@@ -181,6 +182,14 @@ struct bfmmm_sampler {
   vecd tt_ssr, tt_sigma;   // per-slot trace of the last tempered transition
   double last_ssr = 0;     // SSR of the state the last sweep ended with
   int64_t tt_accepts = 0, tt_total = 0;
+  // stored-sample recorder (BFMMM.h:1680-1746)
+  struct Recorder {
+    bool on = false;
+    std::string dir;
+    int r = 0, thin = 1, q = 0;
+    std::vector<vecd> nu, Phi, pi, delta, gamma, A, tau, Z, chi, eta, xi, tau_eta, delta_xi, gamma_xi, A_xi;
+    vecd sigma, alpha3;
+  } rec;
   vecd work, Prec, C, Lc, rhs, v1, v2;
 
   double& nu_(int k, int p) { return nu[(size_t)p * K + k]; }
@@ -727,6 +736,78 @@ int bfmmm_host_update_sigma(bfmmm_sampler* s, double ssr, double beta, int tempe
   return 0;
 }
 
+// ================================================================= stored samples
+// The reference keeps r_stored_iters slots per parameter, slot = iteration % r_stored_iters, and at
+// the end of every batch writes slot 0 and slots thinning*p - 1 (p >= 1) to  dir + Name{q}.txt, then
+// moves the last slot to slot 0 (BFMMM.h:1680-1746).  Only the slots that will be written are kept.
+static bool slot_is_written(const bfmmm_sampler* s, int slot) {
+  if (slot == 0) return true;
+  return ((slot + 1) % s->rec.thin) == 0 && (slot + 1) / s->rec.thin < s->rec.r / s->rec.thin;
+}
+static int record_iteration(bfmmm_sampler* s) {
+  auto& R = s->rec;
+  const int64_t i = s->iteration;
+  const int slot = (int)(i % R.r);
+  if (slot_is_written(s, slot)) {
+    R.nu[slot] = s->nu; R.Phi[slot] = s->Phi; R.pi[slot] = s->pi; R.delta[slot] = s->delta; R.gamma[slot] = s->gamma;
+    R.A[slot] = s->A; R.tau[slot] = s->tau; R.sigma[slot] = s->sigma_sq; R.alpha3[slot] = s->alpha3;
+    if (s->D) { R.eta[slot] = s->eta; R.xi[slot] = s->xi; R.tau_eta[slot] = s->tau_eta; R.delta_xi[slot] = s->delta_xi;
+                R.gamma_xi[slot] = s->gamma_xi; R.A_xi[slot] = s->A_xi; }
+    R.Z[slot].resize((size_t)s->n * s->K); R.chi[slot].resize((size_t)s->n * s->M);
+    if (bfmmm_get_state(s->e, R.Z[slot].data(), R.chi[slot].data())) return 1;
+  }
+  if (((i + 1) % R.r) != 0 || i <= 1) return 0;
+  // ---- write the batch
+  const int ns = R.r / R.thin;
+  const int K = s->K, P = s->P, M = s->M, D = s->D, n = s->n;
+  auto slot_of = [&](int p) { return p == 0 ? 0 : R.thin * p - 1; };
+  auto gather = [&](const std::vector<vecd>& src, size_t per) {
+    vecd out(per * ns);
+    for (int p = 0; p < ns; p++) std::copy(src[slot_of(p)].begin(), src[slot_of(p)].begin() + per, out.begin() + per * p);
+    return out;
+  };
+  const std::string q = std::to_string(R.q);
+  auto path = [&](const char* name) { return R.dir + name + q + ".txt"; };
+  vecd v;
+  v = gather(R.nu, (size_t)K * P);    if (bfmmm_save_cube_txt(path("Nu").c_str(), v.data(), K, P, ns)) return 1;
+  v = gather(R.chi, (size_t)n * M);   if (bfmmm_save_cube_txt(path("Chi").c_str(), v.data(), n, M, ns)) return 1;
+  v = gather(R.pi, (size_t)K);        if (bfmmm_save_mat_txt(path("Pi").c_str(), v.data(), K, ns)) return 1;
+  v.assign(ns, 0.0);                  // alpha_31(0) is never assigned in the reference (:1685,1695-1704)
+  for (int p = 1; p < ns; p++) v[p] = R.alpha3[slot_of(p)];
+  if (bfmmm_save_mat_txt(path("alpha_3").c_str(), v.data(), ns, 1)) return 1;
+  v = gather(R.A, (size_t)K * 2);     if (bfmmm_save_cube_txt(path("A").c_str(), v.data(), K, 2, ns)) return 1;
+  v = gather(R.delta, (size_t)K * M); if (bfmmm_save_cube_txt(path("Delta").c_str(), v.data(), K, M, ns)) return 1;
+  v.assign(ns, 0.0);
+  for (int p = 0; p < ns; p++) v[p] = R.sigma[slot_of(p)];
+  if (bfmmm_save_mat_txt(path("Sigma").c_str(), v.data(), ns, 1)) return 1;
+  v.assign((size_t)ns * K, 0.0);      // tau1 is (draws x K)
+  for (int p = 0; p < ns; p++) for (int k = 0; k < K; k++) v[(size_t)k * ns + p] = R.tau[slot_of(p)][k];
+  if (bfmmm_save_mat_txt(path("Tau").c_str(), v.data(), ns, K)) return 1;
+  v = gather(R.gamma, (size_t)K * P * M); if (bfmmm_save_field_cube_bin(path("Gamma").c_str(), v.data(), ns, 1, K, P, M)) return 1;
+  v = gather(R.Phi, (size_t)K * P * M);   if (bfmmm_save_field_cube_bin(path("Phi").c_str(), v.data(), ns, 1, K, P, M)) return 1;
+  v = gather(R.Z, (size_t)n * K);     if (bfmmm_save_cube_txt(path("Z").c_str(), v.data(), n, K, ns)) return 1;
+  if (D) {                            // covariate-adjusted drivers add these (BFMMM.h:5152-5168)
+    v = gather(R.eta, (size_t)P * D * K);  if (bfmmm_save_field_cube_bin(path("Eta").c_str(), v.data(), ns, 1, P, D, K)) return 1;
+    // field (draws x K) of P x D x M cubes, column-major over the field: k outer
+    auto field_k = [&](const std::vector<vecd>& src) {
+      const size_t per = (size_t)P * D * M;
+      vecd out(per * ns * K);
+      for (int k = 0; k < K; k++)
+        for (int p = 0; p < ns; p++)
+          std::copy(src[slot_of(p)].begin() + per * k, src[slot_of(p)].begin() + per * (k + 1), out.begin() + per * ((size_t)k * ns + p));
+      return out;
+    };
+    v = field_k(R.xi);        if (bfmmm_save_field_cube_bin(path("Xi").c_str(), v.data(), ns, K, P, D, M)) return 1;
+    v = field_k(R.gamma_xi);  if (bfmmm_save_field_cube_bin(path("Gamma_Xi").c_str(), v.data(), ns, K, P, D, M)) return 1;
+    v = gather(R.delta_xi, (size_t)K * M * D); if (bfmmm_save_field_cube_bin(path("Delta_Xi").c_str(), v.data(), ns, 1, K, M, D)) return 1;
+    v = gather(R.A_xi, (size_t)K * 2 * D);     if (bfmmm_save_field_cube_bin(path("A_Xi").c_str(), v.data(), ns, 1, K, 2, D)) return 1;
+    v = gather(R.tau_eta, (size_t)K * D);      if (bfmmm_save_cube_txt(path("Tau_Eta").c_str(), v.data(), K, D, ns)) return 1;
+  }
+  // slot 0 <- last slot (:1733-1745)
+  R.q++;
+  return 0;
+}
+
 // ================================================================= driver loops
 int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   if (!s) return sfail("null sampler");
@@ -797,7 +878,10 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
     s->loglik = -s->n_points_total * (0.918938533204672741780329736406 + 0.5 * std::log(s->sigma_sq)) -
                 ssr_ll / (2 * s->sigma_sq);
   s->tick++;
-  if (!s->in_tt) s->iteration++;
+  if (!s->in_tt) {
+    if (s->rec.on && record_iteration(s)) return 1;
+    s->iteration++;
+  }
   return 0;
 }
 
@@ -854,6 +938,7 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
     s->tt_ssr = tssr; s->tt_sigma = tsig; s->tick = tk; s->tt_accepts = acc; s->tt_total = tot; s->rng = rng;
     if (bfmmm_state_restore(s->e)) return 1;
   }
+  if (s->rec.on && record_iteration(s)) return 1;
   s->iteration++;                                  // a transition is one outer iteration (BFMMM.h:1500)
   if (logA_out) *logA_out = logA;
   if (accepted) *accepted = ok ? 1 : 0;
@@ -875,6 +960,22 @@ int bfmmm_sampler_run_mtt(bfmmm_sampler* s, int n_iter, int n_temp_trans, int N_
   }
   return 0;
 }
+// start writing the reference's stored-sample files: a batch every r_stored_iters iterations,
+// keeping every thinning_num-th draw
+int bfmmm_sampler_record(bfmmm_sampler* s, const char* directory, int r_stored_iters, int thinning_num) {
+  if (!s || !s->e) return sfail("null sampler");
+  if (!directory || r_stored_iters < 2 || thinning_num < 1 || r_stored_iters / thinning_num < 1)
+    return sfail("bfmmm_sampler_record: need a directory, r_stored_iters >= 2 and 1 <= thinning_num <= r_stored_iters");
+  auto& R = s->rec;
+  R.on = true; R.dir = directory; R.r = r_stored_iters; R.thin = thinning_num; R.q = 0;
+  for (auto* v : {&R.nu, &R.Phi, &R.pi, &R.delta, &R.gamma, &R.A, &R.tau, &R.Z, &R.chi, &R.eta, &R.xi, &R.tau_eta,
+                  &R.delta_xi, &R.gamma_xi, &R.A_xi})
+    v->assign(r_stored_iters, vecd());
+  R.sigma.assign(r_stored_iters, 0.0); R.alpha3.assign(r_stored_iters, 0.0);
+  return 0;
+}
+int bfmmm_sampler_batches_written(bfmmm_sampler* s) { return s ? s->rec.q : -1; }
+
 int bfmmm_sampler_tt_trace(bfmmm_sampler* s, double* ssr, double* sigma, int n) {
   if (!s) return sfail("null sampler");
   for (int i = 0; i < n && i < (int)s->tt_ssr.size(); i++) { ssr[i] = s->tt_ssr[i]; sigma[i] = s->tt_sigma[i]; }

@@ -143,6 +143,14 @@ class Sampler:
         self._chk(self._lib.bfmmm_sampler_run_mtt(self._h, int(n_iter), int(n_temp_trans), int(N_t),
                                                   C.c_double(beta_N_t)))
 
+    def record(self, directory, r_stored_iters, thinning_num=1):
+        d = directory if directory.endswith("/") else directory + "/"
+        self._chk(self._lib.bfmmm_sampler_record(self._h, d.encode(), int(r_stored_iters), int(thinning_num)))
+
+    @property
+    def batches_written(self):
+        return int(self._lib.bfmmm_sampler_batches_written(self._h))
+
     def tt_trace(self, N_t):
         n = 2 * N_t + 1
         ssr, sig = np.zeros(n), np.zeros(n)

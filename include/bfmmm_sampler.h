@@ -85,6 +85,11 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
 /* n iterations with the reference's schedule: a tempered transition replaces the sweep whenever
  * the iteration index is a positive multiple of n_temp_trans (0 = never, UserFunctions.cpp:1353-1359) */
 int bfmmm_sampler_run_mtt(bfmmm_sampler* s, int n_iter, int n_temp_trans, int N_t, double beta_N_t);
+/* write the reference's stored-sample files (include/bfmmm_io.h; BFMMM.h:1680-1746): one batch
+ * directory + {Nu,Chi,Pi,alpha_3,A,Delta,Sigma,Tau,Z,Gamma,Phi}{q}.txt every r_stored_iters iterations,
+ * keeping slot 0 and every thinning_num-th draw, exactly like BFMMM_MTT_warm_start */
+int bfmmm_sampler_record(bfmmm_sampler* s, const char* directory, int r_stored_iters, int thinning_num);
+int bfmmm_sampler_batches_written(bfmmm_sampler* s);
 /* per-slot (SSR, sigma^2) of the last tempered transition, slots 0..2*N_t */
 int bfmmm_sampler_tt_trace(bfmmm_sampler* s, double* ssr, double* sigma, int n);
 int64_t bfmmm_sampler_iteration(bfmmm_sampler* s);

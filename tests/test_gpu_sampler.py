@@ -142,3 +142,33 @@ def test_config1_sigma_matches_reference_stored_chain():
     lo, mid, hi = S["Functional_sigma_q"]
     assert lo * 0.9 < med < hi * 1.1, (med, lo, hi)
     smp.close(); eng.close()
+
+
+def test_recorder_writes_reference_batches(tmp_path):
+    """BFMMM.h:1680-1746: slot 0 and every thinning_num-th draw of each r_stored_iters batch."""
+    from bayesfmmm_b200 import io as bio
+    s, eng, smp = _functional(seed=10, n=64)
+    r, thin = 20, 5
+    smp.record(str(tmp_path), r, thin)
+    sig, a3, Zs = [], [], []
+    for it in range(2 * r):
+        smp.step(bf.SWEEP_FULL)
+        g = smp.get()
+        sig.append(g["sigma_sq"]); a3.append(g["alpha3"]); Zs.append(eng.get_state(chi=False)[0])
+    assert smp.batches_written == 2
+    for q in range(2):
+        keep = [q * r] + [q * r + thin * p - 1 for p in range(1, r // thin)]
+        S = bio.load(str(tmp_path / f"Sigma{q}.txt"))
+        assert S.shape == (r // thin, 1) and np.array_equal(S.ravel(), np.array(sig)[keep])
+        A3 = bio.load(str(tmp_path / f"alpha_3{q}.txt")).ravel()
+        assert A3[0] == 0.0 and np.array_equal(A3[1:], np.array(a3)[keep[1:]])
+        Z = bio.load(str(tmp_path / f"Z{q}.txt"))
+        assert Z.shape == (64, s["K"], r // thin)
+        for p, i in enumerate(keep):
+            assert np.array_equal(Z[:, :, p], Zs[i])
+        assert bio.load(str(tmp_path / f"Nu{q}.txt")).shape == (s["K"], s["P"], r // thin)
+        assert bio.load(str(tmp_path / f"Phi{q}.txt")).shape == (r // thin, 1, s["K"], s["P"], s["M"])
+        assert bio.load(str(tmp_path / f"Tau{q}.txt")).shape == (r // thin, s["K"])
+        for name in ("Chi", "Pi", "A", "Delta", "Gamma"):
+            assert os.path.exists(str(tmp_path / f"{name}{q}.txt"))
+    smp.close(); eng.close()
