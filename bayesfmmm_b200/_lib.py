@@ -26,9 +26,9 @@ EXPORTS = [
     "bfmmm_set_state", "bfmmm_get_state", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
     "bfmmm_ssr", "bfmmm_suffstats", "bfmmm_get_gram", "bfmmm_seed", "bfmmm_stats_buffer_dev",
     "bfmmm_update_z_async", "bfmmm_update_chi_async", "bfmmm_ssr_async", "bfmmm_suffstats_async",
-    "bfmmm_read_stats", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts",
+    "bfmmm_read_stats", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts", "bfmmm_suffstats_ragged",
     # include/bfmmm_sampler.h
-    "bfmmm_hyper_defaults", "bfmmm_sampler_create", "bfmmm_sampler_create_detached", "bfmmm_sampler_destroy", "bfmmm_sampler_set_allreduce",
+    "bfmmm_hyper_defaults", "bfmmm_sampler_create", "bfmmm_sampler_create_detached", "bfmmm_sampler_destroy", "bfmmm_sampler_set_allreduce", "bfmmm_sampler_set_hband", "bfmmm_sampler_set_counts",
     "bfmmm_sampler_set", "bfmmm_sampler_get", "bfmmm_sampler_set_cov", "bfmmm_sampler_get_cov",
     "bfmmm_sampler_step", "bfmmm_sampler_run", "bfmmm_sampler_iteration", "bfmmm_sampler_last_accept",
     "bfmmm_sampler_tape", "bfmmm_sampler_tape_left", "bfmmm_sampler_tempered_transition",

@@ -21,7 +21,9 @@ constexpr int RED_MAX = 8;      // values reduced per block in the per-function 
 
 struct PassArgs {
   int n, ld, P, D, QS;
-  const double* __restrict__ Ct;
+  const double* __restrict__ Ct;    // common basis: whitened c~ ; ragged grids: least-squares c_i
+  const double* __restrict__ Gl;    // ragged grids: lower band of G_i, row (j*P + p) = G_i[p-j][p]; else nullptr
+  int bw;                           // ragged grids: band width (degree + 1)
   const double* __restrict__ rss;
   double* __restrict__ Z;
   double* __restrict__ chi;
@@ -186,6 +188,10 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) 
 }
 
 // launchers implemented in the per-kernel translation units
+constexpr int BWMAX = 6;        // ragged grids: band width supported by the per-iteration kernels (degree <= 5)
+int launch_z_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_chi_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_ssr_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
@@ -214,6 +220,31 @@ struct ProjectArgs {
   double* __restrict__ rss;          // [ld]
 };
 int launch_project(const ProjectArgs& a, cudaStream_t s);
+struct RaggedPrepArgs {
+  int n, ld, P, bw, degree, n_knots; int64_t i_begin;
+  const int64_t* __restrict__ off;   // n+1 offsets (relative to the y / t / Brows pointers given here)
+  const double* __restrict__ y;
+  const double* __restrict__ t;      // grid points (spline description) or nullptr
+  const double* __restrict__ knots;  // clamped knot vector or nullptr
+  const double* __restrict__ Brows;  // user-supplied basis rows (row-major) or nullptr
+  double* __restrict__ C;            // [P][ld] least-squares coefficients
+  double* __restrict__ H;            // [P][ld] B_i'y_i
+  double* __restrict__ Gl;           // [bw*P][ld] lower band of G_i
+  double* __restrict__ rss;          // [ld]
+};
+int launch_ragged_prep(const RaggedPrepArgs& a, cudaStream_t s);
+struct RaggedStatsArgs {
+  int n, ld, P, bw, K, M, D, q, npairs;
+  const double* __restrict__ Gl;
+  const double* __restrict__ Z;
+  const double* __restrict__ chi;
+  const double* __restrict__ X;
+  double* __restrict__ partials;
+  double* __restrict__ Hb;          // [npairs][bw*P], pair (a <= b) in row-major upper-triangle order
+};
+int launch_ragged_stats(const RaggedStatsArgs& a, int sm_count, cudaStream_t s);
+size_t ragged_stats_partial_doubles(int P, int bw, int q, int sm_count);
+int launch_band_width(const double* B, int64_t rows, int P, int* bw_dev, cudaStream_t s);
 int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots, int degree, int P,
                    double* B_rowmajor, cudaStream_t s);
 

@@ -38,6 +38,9 @@ struct bfmmm_engine {
   int sm_count = 148;
   // device
   double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
+  double *Hh = nullptr, *Gl = nullptr, *rs_partials = nullptr;   // ragged grids: B_i'y_i, band of G_i
+  int bw = 0, npairs = 0;
+  bool ragged = false;
   double *snapZ = nullptr, *snapChi = nullptr;   // device copy of (Z, chi) for tempered transitions
   double *draws = nullptr, *stats = nullptr, *partials = nullptr, *st_partials = nullptr, *acc_dbg = nullptr;
   unsigned int* ticket = nullptr;
@@ -58,6 +61,7 @@ struct bfmmm_engine {
   int off_ssr_after() const { return K + 2; }
   int off_wtw() const { return K + 3; }
   int off_ctw() const { return K + 3 + q * q; }
+  int off_hb() const { return K + 3 + q * q + P * q; }
 };
 
 namespace {
@@ -85,6 +89,7 @@ void free_all(bfmmm_engine* e) {
   cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
   cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
   cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi);
+  cudaFree(e->Hh); cudaFree(e->Gl); cudaFree(e->rs_partials);
   for (int i = 0; i < N_STAGE; i++) {
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
@@ -175,6 +180,68 @@ int project_common(bfmmm_engine* e, const bfmmm_config* c) {
   return 0;
 }
 
+// ragged grids: per-function banded Gram, least-squares coefficients, B_i'y_i, orthogonal residual
+int project_ragged(bfmmm_engine* e, const bfmmm_config* c) {
+  const int P = e->P, n = e->n;
+  if (!c->off) return fail("bfmmm_create: ragged grids need the offsets `off`");
+  const int64_t N = c->off[n] - c->off[0];
+  if (N <= 0) return fail("bfmmm_create: empty observations");
+  double sum_half = 0;
+  for (int i = 0; i < n; i++) {
+    int64_t ni = c->off[i + 1] - c->off[i];
+    if (ni < 0) return fail("bfmmm_create: offsets must be non-decreasing");
+    sum_half += (double)(ni / 2);                              // integer division, UpdateSigma.h:49
+  }
+  e->n_points = (double)N; e->sum_half = sum_half;
+  std::vector<int64_t> off(c->off, c->off + n + 1);
+  for (auto& o : off) o -= c->off[0];
+  int64_t* d_off = nullptr; double *d_y = nullptr, *d_t = nullptr, *d_B = nullptr, *d_kn = nullptr; int* d_bw = nullptr;
+  CU(cudaMalloc(&d_off, (size_t)(n + 1) * 8)); CU(cudaMalloc(&d_y, (size_t)N * 8));
+  CU(cudaMemcpyAsync(d_off, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(d_y, c->y + c->off[0], (size_t)N * 8, cudaMemcpyHostToDevice, e->stream));
+  bf::RaggedPrepArgs pa;
+  std::memset(&pa, 0, sizeof(pa));
+  std::vector<double> kn;
+  if (c->B) {
+    CU(cudaMalloc(&d_B, (size_t)N * P * 8));
+    CU(cudaMemcpyAsync(d_B, c->B + (size_t)c->off[0] * P, (size_t)N * P * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMalloc(&d_bw, 4)); CU(cudaMemsetAsync(d_bw, 0, 4, e->stream));
+    if (bf::launch_band_width(d_B, N, P, d_bw, e->stream)) return fail("band width kernel launch failed");
+    CU(cudaMemcpyAsync(&e->bw, d_bw, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->bw < 1) e->bw = 1;
+    pa.Brows = d_B;
+  } else {
+    if (!c->t || (c->n_internal > 0 && !c->internal_knots)) return fail("bfmmm_create: neither B nor a spline description (t, knots) was given");
+    if (c->n_internal + c->degree + 1 != P) return fail("bfmmm_create: P != n_internal + degree + 1");
+    int nk = c->n_internal + 2 * (c->degree + 1);
+    kn.resize(nk);
+    for (int i = 0; i <= c->degree; i++) { kn[i] = c->boundary[0]; kn[nk - 1 - i] = c->boundary[1]; }
+    for (int i = 0; i < c->n_internal; i++) kn[c->degree + 1 + i] = c->internal_knots[i];
+    CU(cudaMalloc(&d_t, (size_t)N * 8)); CU(cudaMalloc(&d_kn, (size_t)nk * 8));
+    CU(cudaMemcpyAsync(d_t, c->t + c->off[0], (size_t)N * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_kn, kn.data(), (size_t)nk * 8, cudaMemcpyHostToDevice, e->stream));
+    e->bw = c->degree + 1;
+    pa.t = d_t; pa.knots = d_kn; pa.n_knots = nk; pa.degree = c->degree;
+  }
+  if (e->bw > bf::BWMAX) return fail("bfmmm_create: ragged grids support a basis band width (degree + 1) of at most 6");
+  if (e->bw > P) e->bw = P;
+  CU(cudaMalloc(&e->Hh, (size_t)e->ld * P * 8));
+  CU(cudaMalloc(&e->Gl, (size_t)e->ld * P * e->bw * 8));
+  CU(cudaMemsetAsync(e->Hh, 0, (size_t)e->ld * P * 8, e->stream));
+  CU(cudaMemsetAsync(e->Gl, 0, (size_t)e->ld * P * e->bw * 8, e->stream));
+  pa.n = n; pa.ld = e->ld; pa.P = P; pa.bw = e->bw; pa.i_begin = 0; pa.off = d_off; pa.y = d_y;
+  pa.C = e->Ct; pa.H = e->Hh; pa.Gl = e->Gl; pa.rss = e->rss;
+  int rc = bf::launch_ragged_prep(pa, e->stream);
+  if (rc) return fail("ragged prep kernel launch failed (P <= 64 and band width <= 8 supported) rc=" + std::to_string(rc));
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFree(d_off); cudaFree(d_y); cudaFree(d_t); cudaFree(d_B); cudaFree(d_kn); cudaFree(d_bw);
+  // statistics: pair cross-Gram
+  e->npairs = e->q * (e->q + 1) / 2;
+  CU(cudaMalloc(&e->rs_partials, bf::ragged_stats_partial_doubles(P, e->bw, e->q, e->sm_count) * 8));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -204,8 +271,9 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   e->ld = (c->n + 7) & ~7;
   e->q = c->K * (1 + c->D) * (1 + c->M);
   e->QS = (e->q + 1) & ~1;
-  if (!e->common) { delete e; return fail("bfmmm_create: ragged grids are not supported by this build yet"); }
-  if (!e->identity && e->T < 1) { delete e; return fail("bfmmm_create: common grid needs T >= 1"); }
+  e->ragged = !e->common;
+  if (e->common && !e->identity && e->T < 1) { delete e; return fail("bfmmm_create: common grid needs T >= 1"); }
+  if (e->ragged && (e->q > 40 || e->P > 64)) { delete e; return fail("bfmmm_create: ragged grids support P <= 64 and q = K(1+D)(1+M) <= 40"); }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, c->device);
   e->sm_count = prop.multiProcessorCount;
@@ -225,6 +293,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMalloc(&e->glob, (size_t)e->P * e->QS * 8));
   CUE(cudaMalloc(&e->draws, ld * (std::max(e->K + 1, e->M)) * 8));
   e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q;
+  if (e->ragged) e->stats_len += (int64_t)(e->q * (e->q + 1) / 2) * bf::BWMAX * e->P;   // upper bound (bw <= BWMAX)
   CUE(cudaMalloc(&e->stats, e->stats_len * 8));
   e->pass_blocks = bf::pass_grid(e->ld, 1);
   CUE(cudaMalloc(&e->partials, (size_t)e->pass_blocks * bf::RED_MAX * 8));
@@ -251,6 +320,12 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     if (upload_cols(e, e->Ct, c->y, e->P)) return bail(1);      // c~_i = y_i, rss_i = 0
     e->n_points = (double)e->n * e->P;
     e->sum_half = (double)(((int64_t)e->n * e->P) / 2);          // y_obs.n_elem / 2, UpdateSigma.h:150
+  } else if (e->ragged) {
+    e->G.assign((size_t)e->P * e->P, 0.0);
+    e->L.assign((size_t)e->P * e->P, 0.0);
+    for (int p = 0; p < e->P; p++) e->L[(size_t)p * e->P + p] = 1;      // no common whitening
+    if (project_ragged(e, c)) return bail(1);
+    e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q + (int64_t)e->npairs * e->bw * e->P;
   } else {
     if (build_basis(e, c)) return bail(1);
     if (project_common(e, c)) return bail(1);
@@ -274,6 +349,7 @@ int bfmmm_get_basis(bfmmm_engine* e, double* B_out) {
 int bfmmm_engine_dims(bfmmm_engine* e, int32_t* dims) {
   if (!e || !dims) return fail("null argument");
   dims[0] = e->n; dims[1] = e->K; dims[2] = e->P; dims[3] = e->M; dims[4] = e->D; dims[5] = e->model;
+  dims[6] = e->ragged ? 1 : 0; dims[7] = e->bw;
   return 0;
 }
 int bfmmm_counts(bfmmm_engine* e, double* sum_half, double* n_points) {
@@ -284,6 +360,7 @@ int bfmmm_counts(bfmmm_engine* e, double* sum_half, double* n_points) {
 }
 int bfmmm_get_gram(bfmmm_engine* e, double* G) {
   if (!e) return fail("null engine");
+  if (e->ragged) return fail("bfmmm_get_gram: ragged grids have one Gram matrix per function (use bfmmm_suffstats_ragged)");
   std::copy(e->G.begin(), e->G.end(), G);
   return 0;
 }
@@ -328,7 +405,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
       else v = xi[(size_t)k * P * D * M + ((size_t)(mm - 1) * D + (dd - 1)) * P + p];
       cvec[p] = v;
     }
-    if (e->identity) {
+    if (e->identity || e->ragged) {
       for (int p = 0; p < P; p++) h[(size_t)p * QS + f] = cvec[p];
     } else {
       for (int p = 0; p < P; p++) {
@@ -349,7 +426,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
 static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
   a.n = e->n; a.ld = e->ld; a.P = e->P; a.D = e->D; a.QS = e->QS;
-  a.Ct = e->Ct; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
+  a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
   a.sigma_sq = e->sigma_sq; a.beta = beta;
   a.key = e->key; a.iteration = e->iteration; a.global_offset = (uint64_t)e->global_offset;
   a.partials = e->partials; a.ticket = e->ticket;
@@ -365,7 +442,7 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
   if (dump_draws) a.draws_out = e->draws;
   a.acc_out = e->acc_dbg;
   a.out = e->stats + e->off_slz(); a.n_out = e->K + 1;
-  int rc = bf::launch_z(a, e->K, e->M, e->stream);
+  int rc = e->ragged ? bf::launch_z_ragged(a, e->K, e->M, e->stream) : bf::launch_z(a, e->K, e->M, e->stream);
   if (rc) return fail("z kernel launch failed rc=" + std::to_string(rc));
   return 0;
 }
@@ -398,7 +475,7 @@ static int chi_launch(bfmmm_engine* e, double beta, bool injected) {
   fill_pass(e, a, beta);
   if (injected) a.eps = e->draws;
   a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
-  int rc = bf::launch_chi(a, e->K, e->M, e->stream);
+  int rc = e->ragged ? bf::launch_chi_ragged(a, e->K, e->M, e->stream) : bf::launch_chi(a, e->K, e->M, e->stream);
   if (rc) return fail("chi kernel launch failed rc=" + std::to_string(rc));
   return 0;
 }
@@ -424,7 +501,7 @@ int bfmmm_ssr_async(bfmmm_engine* e) {
   bf::PassArgs a;
   fill_pass(e, a, 1.0);
   a.out = e->stats + e->off_ssr(); a.n_out = 1;
-  int rc = bf::launch_ssr(a, e->K, e->M, e->stream);
+  int rc = e->ragged ? bf::launch_ssr_ragged(a, e->K, e->M, e->stream) : bf::launch_ssr(a, e->K, e->M, e->stream);
   if (rc) return fail("ssr kernel launch failed rc=" + std::to_string(rc));
   return 0;
 }
@@ -443,10 +520,17 @@ int bfmmm_suffstats_async(bfmmm_engine* e) {
   CU(cudaSetDevice(e->device));
   bf::StatsArgs a;
   a.n = e->n; a.ld = e->ld; a.P = e->P; a.K = e->K; a.M = e->M; a.D = e->D; a.q = e->q;
-  a.Ct = e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
+  a.Ct = e->ragged ? e->Hh : e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
   a.WtW = e->stats + e->off_wtw(); a.CtW = e->stats + e->off_ctw(); a.blocks = e->st_blocks;
   int rc = bf::launch_stats(a, e->stream);
   if (rc) return fail("stats kernel launch failed rc=" + std::to_string(rc));
+  if (e->ragged) {
+    bf::RaggedStatsArgs r;
+    r.n = e->n; r.ld = e->ld; r.P = e->P; r.bw = e->bw; r.K = e->K; r.M = e->M; r.D = e->D; r.q = e->q; r.npairs = e->npairs;
+    r.Gl = e->Gl; r.Z = e->Z; r.chi = e->chi; r.X = e->X; r.partials = e->rs_partials; r.Hb = e->stats + e->off_hb();
+    rc = bf::launch_ragged_stats(r, e->sm_count, e->stream);
+    if (rc) return fail("ragged stats kernel launch failed rc=" + std::to_string(rc));
+  }
   return 0;
 }
 
@@ -455,7 +539,7 @@ static void unwhiten(const bfmmm_engine* e, const double* CtW, double* BtYW) {
   const int P = e->P;
   for (int f = 0; f < e->q; f++)
     for (int r = 0; r < P; r++) {
-      if (e->identity) { BtYW[(size_t)f * P + r] = CtW[(size_t)f * P + r]; continue; }
+      if (e->identity || e->ragged) { BtYW[(size_t)f * P + r] = CtW[(size_t)f * P + r]; continue; }
       double s = 0;
       for (int k = 0; k <= r; k++) s += e->L[(size_t)k * P + r] * CtW[(size_t)f * P + k];
       BtYW[(size_t)f * P + r] = s;
@@ -488,6 +572,18 @@ int bfmmm_state_restore(bfmmm_engine* e) {
   CU(cudaSetDevice(e->device));
   CU(cudaMemcpyAsync(e->Z, e->snapZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
   CU(cudaMemcpyAsync(e->chi, e->snapChi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+
+int bfmmm_suffstats_ragged(bfmmm_engine* e, double* WtW, double* BtYW, double* Hband) {
+  if (!e || !e->ragged) return fail("bfmmm_suffstats_ragged: engine was not created with ragged grids");
+  if (bfmmm_suffstats_async(e)) return 1;
+  const int64_t len = e->stats_len - e->off_wtw();
+  CU(cudaMemcpyAsync(e->h_stats + e->off_wtw(), e->stats + e->off_wtw(), len * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  if (WtW) std::copy(e->h_stats + e->off_wtw(), e->h_stats + e->off_ctw(), WtW);
+  if (BtYW) std::copy(e->h_stats + e->off_ctw(), e->h_stats + e->off_hb(), BtYW);
+  if (Hband) std::copy(e->h_stats + e->off_hb(), e->h_stats + e->stats_len, Hband);
   return 0;
 }
 
@@ -560,7 +656,8 @@ int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out) {
   fill_pass(e, a, beta);
   a.draws_out = e->draws;
   a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
-  if (bf::launch_chi(a, e->K, e->M, e->stream)) return fail("chi kernel launch failed");
+  if (e->ragged ? bf::launch_chi_ragged(a, e->K, e->M, e->stream) : bf::launch_chi(a, e->K, e->M, e->stream))
+    return fail("chi kernel launch failed");
   if (download_cols(e, eps_out, e->draws, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
   return 0;

@@ -167,7 +167,10 @@ struct bfmmm_sampler {
   bfmmm_engine* e = nullptr;
   bfmmm_hyper h{};
   int n = 0, K = 0, P = 0, M = 0, D = 0, q = 0;
-  bool identity = false;
+  bool identity = false, ragged = false;
+  int bw = 0;
+  const double* Hb = nullptr;   // ragged grids: pair cross-Gram band (set before the block draws)
+  vecd Hb_own;
   int64_t n_total = 0, iteration = 0, last_accept = 0;
   int64_t tick = 0;        // monotone counter keying every random stream (tempered steps advance it too)
   bool in_tt = false;      // inside a tempered transition: sweeps do not advance `iteration`
@@ -236,6 +239,38 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
   const int a = s->feat(k, mm, dd);
   s->Prec.resize((size_t)P * P); s->C.resize((size_t)P * P); s->Lc.resize((size_t)P * P);
   s->rhs.resize(P); s->v1.resize(P); s->v2.resize(P);
+  const double sc = beta / s->sigma_sq;
+  if (s->ragged) {
+    // H_ab = sum_i w_ia w_ib G_i, banded: Hb[pair][j*P + p] = H_ab[p-j][p]
+    if (!s->Hb) return sfail("block draw: ragged sampler has no pair cross-Gram (bfmmm_sampler_set_hband)");
+    const int bw = s->bw;
+    auto pair_index = [&](int x, int y) { if (x > y) std::swap(x, y); return x * q - x * (x - 1) / 2 + (y - x); };
+    std::fill(s->v1.begin(), s->v1.end(), 0.0);
+    for (int kk = 0; kk < s->K; kk++)
+      for (int m2 = 0; m2 <= s->M; m2++)
+        for (int d2 = 0; d2 <= s->D; d2++) {
+          int b = s->feat(kk, m2, d2);
+          if (b == a) continue;
+          const double* hb = s->Hb + (size_t)pair_index(a, b) * bw * P;
+          get_coef(s, kk, m2, d2, s->v2.data());
+          for (int p = 0; p < P; p++) {
+            s->v1[p] += hb[p] * s->v2[p];
+            for (int j = 1; j < bw && p - j >= 0; j++) {
+              s->v1[p] += hb[(size_t)j * P + p] * s->v2[p - j];
+              s->v1[p - j] += hb[(size_t)j * P + p] * s->v2[p];
+            }
+          }
+        }
+    for (int r = 0; r < P; r++) s->rhs[r] = sc * (BtYW[(size_t)a * P + r] - s->v1[r]);
+    const double* haa = s->Hb + (size_t)pair_index(a, a) * bw * P;
+    for (int c = 0; c < P; c++)
+      for (int r = 0; r < P; r++) {
+        int lo = r < c ? r : c, hi = r < c ? c : r;
+        double g = (hi - lo < bw) ? haa[(size_t)(hi - lo) * P + hi] : 0.0;
+        double pr = prior_full ? prior_full[(size_t)c * P + r] : (r == c ? prior_diag[r] : 0.0);
+        s->Prec[(size_t)c * P + r] = sc * g + pr;
+      }
+  } else {
   // v1 = sum_{b != a} S_ab c_b
   std::fill(s->v1.begin(), s->v1.end(), 0.0);
   for (int kk = 0; kk < s->K; kk++)
@@ -249,7 +284,6 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
         for (int p = 0; p < P; p++) s->v1[p] += sab * s->v2[p];
       }
   const double saa = WtW[(size_t)a * q + a];
-  const double sc = beta / s->sigma_sq;
   for (int r = 0; r < P; r++) {
     double gv = 0;
     if (s->identity) gv = s->v1[r];
@@ -262,6 +296,7 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
       double pr = prior_full ? prior_full[(size_t)c * P + r] : (r == c ? prior_diag[r] : 0.0);
       s->Prec[(size_t)c * P + r] = sc * saa * g + pr;
     }
+  }
   if (!inv_spd(P, s->Prec.data(), s->C.data(), s->work)) {
     pinv_sym_jacobi(P, s->Prec.data(), s->C.data());
     for (int c = 0; c < P; c++)
@@ -308,6 +343,7 @@ double st_ssr(bfmmm_sampler* s) { return s->stats[s->K + 1]; }
 double st_ssr_after(bfmmm_sampler* s) { return s->stats[s->K + 2]; }
 const double* st_wtw(bfmmm_sampler* s) { return s->stats.data() + s->K + 3; }
 const double* st_btyw(bfmmm_sampler* s) { return s->stats.data() + s->K + 3 + (size_t)s->q * s->q; }
+const double* st_hb(bfmmm_sampler* s) { return s->stats.data() + s->K + 3 + (size_t)s->q * s->q + (size_t)s->P * s->q; }
 
 }  // namespace
 
@@ -327,6 +363,7 @@ static bfmmm_sampler* make_sampler(const int32_t* dims, const bfmmm_hyper* h, in
   s->h = *h;
   s->n = dims[0]; s->K = dims[1]; s->P = dims[2]; s->M = dims[3]; s->D = dims[4];
   s->identity = dims[5] == BFMMM_MULTIVARIATE;
+  s->ragged = dims[6] != 0; s->bw = dims[7];
   s->q = s->K * (1 + s->D) * (1 + s->M);
   s->n_total = n_total > 0 ? n_total : s->n;
   s->rng.key = seed;
@@ -346,17 +383,18 @@ static bfmmm_sampler* make_sampler(const int32_t* dims, const bfmmm_hyper* h, in
 int bfmmm_sampler_create(bfmmm_engine* e, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
                          uint64_t seed, bfmmm_sampler** out) {
   if (!e || !h || !out) return sfail("bfmmm_sampler_create: null argument");
-  int32_t dims[6];
+  int32_t dims[8];
   if (bfmmm_engine_dims(e, dims)) return 1;
   if (dims[5] != BFMMM_MULTIVARIATE && !Pmat) return sfail("bfmmm_sampler_create: the functional model needs the penalty matrix P");
   bfmmm_sampler* s = make_sampler(dims, h, n_total, seed);
   s->e = e;
-  bfmmm_get_gram(e, s->G.data());
+  if (!s->ragged) bfmmm_get_gram(e, s->G.data());
   if (Pmat) s->Pmat.assign(Pmat, Pmat + (size_t)s->P * s->P);
   double sum_half = 0, npts = 0;
   bfmmm_counts(e, &sum_half, &npts);
   // per-shard counts -> whole data set (common grid: every function has the same n_i)
-  double ratio = (double)s->n_total / (double)s->n;
+  double ratio = (double)s->n_total / (double)s->n;   // exact on a common grid; ragged multi-shard runs
+                                                       // set the totals with bfmmm_sampler_set_counts
   s->n_points_total = npts * ratio;
   s->sum_half_total = s->identity ? (double)(((int64_t)s->n_total * s->P) / 2) : sum_half * ratio;
   *out = s;
@@ -376,6 +414,22 @@ int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int
   return 0;
 }
 void bfmmm_sampler_destroy(bfmmm_sampler* s) { delete s; }
+// ragged grids: pair cross-Gram band for the bfmmm_host_update_{phi,nu,eta,xi} calls that follow
+// (copied); bfmmm_sampler_step sets it from the device statistics itself
+int bfmmm_sampler_set_hband(bfmmm_sampler* s, const double* Hband) {
+  if (!s || !s->ragged) return sfail("bfmmm_sampler_set_hband: not a ragged-grid sampler");
+  size_t len = (size_t)(s->q * (s->q + 1) / 2) * s->bw * s->P;
+  s->Hb_own.assign(Hband, Hband + len);
+  s->Hb = s->Hb_own.data();
+  return 0;
+}
+// totals over ALL shards of sum_i floor(n_i/2) and sum_i n_i (ragged multi-GPU runs all-reduce the
+// per-shard bfmmm_counts once and set them here)
+int bfmmm_sampler_set_counts(bfmmm_sampler* s, double sum_half_total, double n_points_total) {
+  if (!s) return sfail("null sampler");
+  s->sum_half_total = sum_half_total; s->n_points_total = n_points_total;
+  return 0;
+}
 int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx) {
   if (!s) return sfail("null sampler");
   s->allreduce = fn; s->allreduce_ctx = ctx;
@@ -827,6 +881,7 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   // the sufficient statistics depend only on (Z, chi, X): one pass feeds Phi, nu, eta and xi
   if (bfmmm_suffstats_async(e)) return 1;
   if (reduce_and_read(s)) return 1;
+  if (s->ragged) s->Hb = st_hb(s);
   if (do_z) {
     s->last_accept = (int64_t)std::llround(st_acc(s));
     if (bfmmm_host_update_pi(s, st_slz(s))) return 1;
@@ -856,6 +911,7 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
     // xi block with its shrinkage priors -- chi has changed, so the statistics are taken again
     if (bfmmm_suffstats_async(e)) return 1;
     if (reduce_and_read(s)) return 1;
+    if (s->ragged) s->Hb = st_hb(s);
     if (do_nu && bfmmm_host_update_eta(s, st_wtw(s), st_btyw(s), beta)) return 1;
     if (bfmmm_host_update_tau_eta(s)) return 1;
     if (do_phi) {

@@ -26,39 +26,87 @@ template <int V> __device__ __forceinline__ void stv(double* p, const double (&o
 // Streams the P rows of the coefficient cache for the V functions of this thread with the loads of
 // the NEXT group of CH rows in flight while the current group is consumed (software pipelining:
 // without it the passes sit on long-scoreboard stalls, see profiles/).  Loads are ld.global.cs
-// (streamed once per pass, evict-first).
-template <int V, int CH, typename F>
-__device__ __forceinline__ void stream_rows(const double* __restrict__ base, int ld, int P, int i0, F&& body) {
+// (streamed once per pass, evict-first).  NB > 0 (ragged grids) also streams, for every row p, the
+// bw <= NB band rows Gl[j*P + p] of the per-function Gram matrices.
+template <int V, int CH, int NB, typename F>
+__device__ __forceinline__ void stream_rows(const double* __restrict__ base, const double* __restrict__ band, int bw,
+                                            int ld, int P, int i0, F&& body) {
   double cur[CH][V], nxt[CH][V];
+  double gcur[CH][NB > 0 ? NB : 1][V], gnxt[CH][NB > 0 ? NB : 1][V];
   const double* col = base + i0;
+  const double* bcol = band + i0;
+  auto fetch = [&](int p, double (&c)[V], double (&g)[NB > 0 ? NB : 1][V]) {
+    if (p < P) {
+      ldv_cs<V>(col + (size_t)p * ld, c);
+      if constexpr (NB > 0) {
 #pragma unroll
-  for (int j = 0; j < CH; j++) {
-    if (j < P) ldv_cs<V>(col + (size_t)j * ld, cur[j]);
-    else {
+        for (int j = 0; j < NB; j++) {
+          if (j < bw) ldv_cs<V>(bcol + ((size_t)j * P + p) * ld, g[j]);
+          else {
 #pragma unroll
-      for (int v = 0; v < V; v++) cur[j][v] = 0.0;
+            for (int v = 0; v < V; v++) g[j][v] = 0.0;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; v++) c[v] = 0.0;
     }
-  }
+  };
+#pragma unroll
+  for (int j = 0; j < CH; j++) fetch(j, cur[j], gcur[j]);
   for (int p0 = 0; p0 < P; p0 += CH) {
 #pragma unroll
+    for (int j = 0; j < CH; j++) fetch(p0 + CH + j, nxt[j], gnxt[j]);
+#pragma unroll
+    for (int j = 0; j < CH; j++)
+      if (p0 + j < P) body(p0 + j, cur[j], gcur[j]);
+#pragma unroll
     for (int j = 0; j < CH; j++) {
-      const int p = p0 + CH + j;
-      if (p < P) ldv_cs<V>(col + (size_t)p * ld, nxt[j]);
-      else {
-#pragma unroll
-        for (int v = 0; v < V; v++) nxt[j][v] = 0.0;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < CH; j++)
-      if (p0 + j < P) body(p0 + j, cur[j]);
-#pragma unroll
-    for (int j = 0; j < CH; j++)
 #pragma unroll
       for (int v = 0; v < V; v++) cur[j][v] = nxt[j][v];
+      if constexpr (NB > 0) {
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+          for (int v = 0; v < V; v++) gcur[j][b][v] = gnxt[j][b][v];
+      }
+    }
   }
 }
-constexpr int ROW_CH = 4;
+
+// Sliding window for the banded quadratic / bilinear forms of the ragged-grid kernels.
+//   x' G y = sum_p [ G[p][p] x_p y_p + sum_{j>=1} G[p-j][p] (x_{p-j} y_p + x_p y_{p-j}) ]
+// prev[j-1] holds the value of the vector at row p - j.
+struct BandWin {
+  double prev[BWMAX - 1];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int j = 0; j < BWMAX - 1; j++) prev[j] = 0.0;
+  }
+  __device__ __forceinline__ void push(double x) {
+#pragma unroll
+    for (int j = BWMAX - 2; j > 0; j--) prev[j] = prev[j - 1];
+    prev[0] = x;
+  }
+};
+// contribution of row p to x' G y (x, y the current values; wx, wy the windows BEFORE pushing p)
+__device__ __forceinline__ double band_term(const double (&g)[BWMAX], double x, double y, const BandWin& wx,
+                                            const BandWin& wy) {
+  double t = g[0] * x * y;
+#pragma unroll
+  for (int j = 1; j < BWMAX; j++) t = fma(g[j], fma(wx.prev[j - 1], y, x * wy.prev[j - 1]), t);
+  return t;
+}
+// x' G x
+__device__ __forceinline__ double band_term_sq(const double (&g)[BWMAX], double x, const BandWin& wx) {
+  double t = g[0] * x;
+#pragma unroll
+  for (int j = 1; j < BWMAX; j++) t = fma(2.0 * g[j], wx.prev[j - 1], t);
+  return t * x;
+}
+constexpr int ROW_CH = 4;       // rows in flight ahead (common basis)
+constexpr int ROW_CH_RAGGED = 2; // ragged grids: every row also brings bw band rows
 
 // log Gamma(x) for x > 0 when lx = log(x) is already known.  For x >= 16 Stirling's series
 //   (x - 1/2) log x - x + log(2 pi)/2 + 1/(12x) - 1/(360x^3) + 1/(1260x^5) - 1/(1680x^7) + 1/(1188x^9)
@@ -164,8 +212,8 @@ __device__ __forceinline__ void stage_globals(const PassArgs& a, double* g) {
 // Z_proposal_density :102-113; rdirichlet Distributions.h:22-45; calc_lB :51-61).
 // The squared-error terms are evaluated in the whitened coefficient space, where
 // ||y - B theta||^2 = rss_i + ||c~_i - theta~||^2 and rss_i cancels in the ratio.
-template <int K, int M, bool COV, int V>
-__global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) z_kernel(const PassArgs a) {
+template <int K, int M, bool COV, int V, bool RG>
+__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
   const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
@@ -222,7 +270,12 @@ __global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) z_kernel(const Pas
 #pragma unroll
     for (int v = 0; v < V; v++) { so[v] = 0; sn[v] = 0; }
     Coef<K, M, COV, V> cf;
-    stream_rows<V, ROW_CH>(a.Ct, a.ld, a.P, i0, [&](int p, const double (&c)[V]) {
+    constexpr int NB = RG ? BWMAX : 0;
+    BandWin wo[V], wn[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { wo[v].clear(); wn[v].clear(); }
+    stream_rows<V, RG ? ROW_CH_RAGGED : ROW_CH, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
+                                                    [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
       for (int v = 0; v < V; v++) {
@@ -235,8 +288,17 @@ __global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) z_kernel(const Pas
           ro = fma(-st.z[v][k], at, ro);
           rn = fma(-zp[v][k], at, rn);
         }
-        so[v] = fma(ro, ro, so[v]);
-        sn[v] = fma(rn, rn, sn[v]);
+        if constexpr (RG) {       // (c - theta)' G_i (c - theta) through the band of G_i
+          double gv[BWMAX];
+#pragma unroll
+          for (int j = 0; j < BWMAX; j++) gv[j] = gb[j][v];
+          so[v] += band_term_sq(gv, ro, wo[v]);
+          sn[v] += band_term_sq(gv, rn, wn[v]);
+          wo[v].push(ro); wn[v].push(rn);
+        } else {
+          so[v] = fma(ro, ro, so[v]);
+          sn[v] = fma(rn, rn, sn[v]);
+        }
       }
     });
     // ---- acceptance
@@ -299,8 +361,8 @@ __global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) z_kernel(const Pas
 // Gram G[m][n] = ph_m . ph_n and r[m] = ph_m . (y - B mu) are accumulated once (in coefficient
 // space), then the reference's sequential m = 0..M-1 sweep is run on them, so chi(i,n) for n < m
 // is the already-updated value exactly as in UpdateChi.h:48.
-template <int K, int M, bool COV, int V>
-__global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) chi_kernel(const PassArgs a) {
+template <int K, int M, bool COV, int V, bool RG>
+__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
   const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
@@ -320,7 +382,16 @@ __global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) chi_kernel(const P
       }
     }
     Coef<K, M, COV, V> cf;
-    stream_rows<V, ROW_CH>(a.Ct, a.ld, a.P, i0, [&](int p, const double (&c)[V]) {
+    constexpr int NB = RG ? BWMAX : 0;
+    BandWin wd[V], wu[V][M];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      wd[v].clear();
+#pragma unroll
+      for (int m = 0; m < M; m++) wu[v][m].clear();
+    }
+    stream_rows<V, RG ? ROW_CH_RAGGED : ROW_CH, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
+                                                    [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
       for (int v = 0; v < V; v++) {
@@ -333,12 +404,29 @@ __global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) chi_kernel(const P
 #pragma unroll
           for (int m = 0; m < M; m++) um[m] = fma(st.z[v][k], cf.get(v, k, m + 1), um[m]);
         }
-        d0[v] = fma(dres, dres, d0[v]);
+        if constexpr (RG) {       // the same forms through the band of G_i
+          double gv[BWMAX];
 #pragma unroll
-        for (int m = 0; m < M; m++) {
-          r[v][m] = fma(um[m], dres, r[v][m]);
+          for (int j = 0; j < BWMAX; j++) gv[j] = gb[j][v];
+          d0[v] += band_term_sq(gv, dres, wd[v]);
 #pragma unroll
-          for (int q = m; q < M; q++) G[v][m][q] = fma(um[m], um[q], G[v][m][q]);
+          for (int m = 0; m < M; m++) {
+            r[v][m] += band_term(gv, um[m], dres, wu[v][m], wd[v]);
+            G[v][m][m] += band_term_sq(gv, um[m], wu[v][m]);
+#pragma unroll
+            for (int q = m + 1; q < M; q++) G[v][m][q] += band_term(gv, um[m], um[q], wu[v][m], wu[v][q]);
+          }
+          wd[v].push(dres);
+#pragma unroll
+          for (int m = 0; m < M; m++) wu[v][m].push(um[m]);
+        } else {
+          d0[v] = fma(dres, dres, d0[v]);
+#pragma unroll
+          for (int m = 0; m < M; m++) {
+            r[v][m] = fma(um[m], dres, r[v][m]);
+#pragma unroll
+            for (int q = m; q < M; q++) G[v][m][q] = fma(um[m], um[q], G[v][m][q]);
+          }
         }
       }
     });
@@ -409,7 +497,7 @@ __global__ void __launch_bounds__(PF_THREADS, V == 1 ? 8 : 4) chi_kernel(const P
 
 // ================================================================= residual sum of squares
 // the data pass of updateSigma / calcLikelihood (UpdateSigma.h:36-50, CalculateLikelihood.h:28-42)
-template <int K, int M, bool COV, int V>
+template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
@@ -422,7 +510,12 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
 #pragma unroll
     for (int v = 0; v < V; v++) acc[v] = 0;
     Coef<K, M, COV, V> cf;
-    stream_rows<V, ROW_CH>(a.Ct, a.ld, a.P, i0, [&](int p, const double (&c)[V]) {
+    constexpr int NB = RG ? BWMAX : 0;
+    BandWin wr[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) wr[v].clear();
+    stream_rows<V, RG ? ROW_CH_RAGGED : ROW_CH, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
+                                                    [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
       for (int v = 0; v < V; v++) {
@@ -434,7 +527,15 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
           for (int m = 0; m < M; m++) at = fma(st.chi[v][m], cf.get(v, k, m + 1), at);
           res = fma(-st.z[v][k], at, res);
         }
-        acc[v] = fma(res, res, acc[v]);
+        if constexpr (RG) {
+          double gv[BWMAX];
+#pragma unroll
+          for (int j = 0; j < BWMAX; j++) gv[j] = gb[j][v];
+          acc[v] += band_term_sq(gv, res, wr[v]);
+          wr[v].push(res);
+        } else {
+          acc[v] = fma(res, res, acc[v]);
+        }
       }
     });
     double rssv[V];

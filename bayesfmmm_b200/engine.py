@@ -157,6 +157,19 @@ class Engine:
         self._chk(self._lib.bfmmm_suffstats(self._h, _p(WtW), _p(BtYW)))
         return WtW, BtYW
 
+    def suffstats_ragged(self, bw):
+        npairs = self.q * (self.q + 1) // 2
+        WtW = np.zeros((self.q, self.q), order="F")
+        BtYW = np.zeros((self.P, self.q), order="F")
+        Hb = np.zeros((npairs, bw * self.P))
+        self._chk(self._lib.bfmmm_suffstats_ragged(self._h, _p(WtW), _p(BtYW), _p(Hb)))
+        return WtW, BtYW, Hb
+
+    def dims(self):
+        d = (C.c_int32 * 8)()
+        self._chk(self._lib.bfmmm_engine_dims(self._h, d))
+        return tuple(int(x) for x in d)
+
     def gram(self):
         G = np.zeros((self.P, self.P), order="F")
         self._chk(self._lib.bfmmm_get_gram(self._h, _p(G)))

@@ -63,9 +63,10 @@ class Sampler:
                                                 C.c_uint64(seed), C.byref(self._h))
         else:
             self.engine = None
-            n, K, P, M, D, model = dims
+            dims = tuple(dims) + (0, 0) if len(dims) == 6 else tuple(dims)
+            n, K, P, M, D, model, ragged, bw = dims
             self.K, self.P, self.M, self.D = K, P, M, D
-            d = (C.c_int32 * 6)(*dims)
+            d = (C.c_int32 * 8)(*dims)
             Gf = _f(G) if G is not None else _f(np.eye(P))
             rc = self._lib.bfmmm_sampler_create_detached(d, C.byref(self.hyper), C.c_int64(n_total), _p(Pm), _p(Gf),
                                                          C.c_double(sum_half_total), C.c_double(n_points_total),
@@ -166,6 +167,13 @@ class Sampler:
     def last_accept(self):
         self._lib.bfmmm_sampler_last_accept.restype = C.c_int64
         return int(self._lib.bfmmm_sampler_last_accept(self._h))
+
+    def set_hband(self, Hband):
+        hb = np.ascontiguousarray(Hband, dtype=np.float64)
+        self._chk(self._lib.bfmmm_sampler_set_hband(self._h, _p(hb)))
+
+    def set_counts(self, sum_half_total, n_points_total):
+        self._chk(self._lib.bfmmm_sampler_set_counts(self._h, C.c_double(sum_half_total), C.c_double(n_points_total)))
 
     def set_allreduce(self, fn):
         """fn(dev_ptr:int, n_doubles:int, stream:int) -> None; called on the engine's stream order."""

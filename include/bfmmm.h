@@ -108,7 +108,11 @@ int bfmmm_ssr(bfmmm_engine* e, double* ssr, double* sum_half, double* n_points);
  *   BtYW P x q   column-major  sum_i w_if B_i' y_i
  * common grid / MV only; H_fg = WtW[f,g] * (B'B).  Ragged grids: see bfmmm_suffstats_ragged. */
 int bfmmm_suffstats(bfmmm_engine* e, double* WtW, double* BtYW);
-/* shard geometry: dims = {n, K, P, M, D, model} */
+/* ragged grids: additionally Hband[pair][j*P + p] = sum_i w_ia w_ib G_i[p-j][p] for every feature pair
+ * a <= b (row-major upper triangle, npairs = q(q+1)/2) and the bw = degree+1 stored diagonals j.
+ * BtYW is sum_i w_if B_i'y_i as for the common grid; WtW is returned too. */
+int bfmmm_suffstats_ragged(bfmmm_engine* e, double* WtW, double* BtYW, double* Hband);
+/* shard geometry: dims = {n, K, P, M, D, model, ragged (0/1), band width} (8 ints) */
 int bfmmm_engine_dims(bfmmm_engine* e, int32_t* dims);
 /* the data-only counts of updateSigma: sum_i floor(n_i/2) (UpdateSigma.h:49; MV floor(n*P/2), :150)
  * and sum_i n_i, for this shard; no kernel launch */

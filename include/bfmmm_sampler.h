@@ -53,12 +53,16 @@ typedef int (*bfmmm_allreduce_fn)(void* ctx, double* buf_dev, int64_t len, void*
 int bfmmm_sampler_create(bfmmm_engine* e, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
                          uint64_t seed, bfmmm_sampler** out);
 /* sampler without an engine, for exercising the bfmmm_host_update_* functions on the CPU:
- * dims = {n, K, P, M, D, model}; G = B'B (P x P) or NULL for identity */
+ * dims = {n, K, P, M, D, model, ragged (0/1), band width} (8 ints); G = B'B (P x P) or NULL for identity */
 int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int64_t n_total, const double* Pmat,
                                   const double* G, double sum_half_total, double n_points_total, uint64_t seed,
                                   bfmmm_sampler** out);
 void bfmmm_sampler_destroy(bfmmm_sampler* s);
 int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx);
+/* ragged grids: the pair cross-Gram band (bfmmm_suffstats_ragged) used by the block draws that follow */
+int bfmmm_sampler_set_hband(bfmmm_sampler* s, const double* Hband);
+/* totals over all shards of sum_i floor(n_i/2) and sum_i n_i (defaults: this shard's counts scaled by n_total/n) */
+int bfmmm_sampler_set_counts(bfmmm_sampler* s, double sum_half_total, double n_points_total);
 
 /* current values, Armadillo layouts; NULL pointers are skipped.
  * nu KxP | Phi KxPxM | pi K | delta KxM | gamma KxPxM | A Kx2 | tau K

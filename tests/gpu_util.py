@@ -18,6 +18,10 @@ def engine_for(name, device_basis=False, **kw):
                             X=s["X"], **kw)
     elif kind == "mv":
         eng = bf.Engine(model=MULTIVARIATE, n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], X=s["X"], **kw)
+    elif device_basis:
+        eng = bf.Engine(model=FUNCTIONAL, n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], off=s["off"], t=s["t"],
+                        degree=s["degree"], internal_knots=s["internal_knots"], boundary=s["boundary"], X=s["X"],
+                        common_grid=False, **kw)
     else:
         eng = bf.Engine(model=FUNCTIONAL, n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], B=s["B"], off=s["off"],
                         X=s["X"], common_grid=False, **kw)

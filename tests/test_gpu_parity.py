@@ -9,7 +9,9 @@ from tests.gpu_util import engine_for, rel
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-GPU_CASES = [c for c in cases.CASES if cases.CASES[c][0] != "ragged"]
+GPU_CASES = list(cases.CASES)          # common grid, multivariate, covariate-adjusted and ragged grids
+COMMON_CASES = [c for c in cases.CASES if cases.CASES[c][0] != "ragged"]
+RAGGED_CASES = [c for c in cases.CASES if cases.CASES[c][0] == "ragged"]
 
 
 @pytest.mark.parametrize("name", GPU_CASES)
@@ -88,7 +90,7 @@ def _features(s, d):
     return np.stack(cols, axis=1)
 
 
-@pytest.mark.parametrize("name", GPU_CASES)
+@pytest.mark.parametrize("name", COMMON_CASES)
 def test_suffstats(name):
     s, d, st, eng = engine_for(name)
     W = _features(s, d)
@@ -156,3 +158,37 @@ def test_device_rng_replay(name):
     gam2, u2 = eng.debug_update_z_rng(s["pi"], 1.3, cases.A_Z_PM)
     assert np.array_equal(gam, gam2) and np.array_equal(u, u2)
     eng.close()
+
+
+@pytest.mark.parametrize("name", RAGGED_CASES)
+@pytest.mark.parametrize("device_basis", [False, True])
+def test_suffstats_ragged(name, device_basis):
+    """Ragged grids: pair cross-Gram band sum_i w_ia w_ib G_i and sum_i w_if B_i'y_i (DMMA kernels) against
+    a per-function NumPy evaluation; both the user-supplied-rows and the device-spline create paths."""
+    from tests.test_host_updates import _ragged_stats
+    s, d, st, eng = engine_for(name, device_basis=device_basis)
+    dims = eng.dims()
+    assert dims[6] == 1 and dims[7] == 4
+    WtW, BtYW, Hb = eng.suffstats_ragged(dims[7])
+    WtW_o, BtYW_o, Hb_o = _ragged_stats(s, d)
+    assert rel(WtW, WtW_o) < TOL and rel(BtYW, BtYW_o) < TOL and rel(Hb, Hb_o) < TOL
+    assert rel(eng.ssr()[0], orc.ssr(d, st)[0]) < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("name", RAGGED_CASES)
+def test_ragged_sweep_matches_oracle_updates(name):
+    """One host block draw through the engine's ragged statistics equals the oracle's per-point loops."""
+    import bayesfmmm_b200 as bf
+    s, d, st, eng = engine_for(name)
+    dr = cases.draws(name, s)
+    smp = bf.Sampler(eng, hyper=bf.default_hyper(True), n_total=d.n, Pmat=orc.pmat_rw1(d.P), seed=3)
+    par = s["par"]
+    smp.set(nu=par["nu"], Phi=par["Phi"], sigma_sq=par["sigma_sq"], tau=dr["tau"])
+    if d.D:
+        smp.set_cov(eta=par["eta"], xi=par["xi"], tau_eta=dr["tau_eta"])
+    WtW, BtYW, Hb = eng.suffstats_ragged(4)
+    smp.set_hband(Hb)
+    smp.tape(dr["z_nu"].ravel(order="F")); smp.host_update("nu", WtW, BtYW, 1.0)
+    assert rel(smp.get()["nu"], orc.update_nu(d, st, dr["tau"], orc.pmat_rw1(d.P), dr["z_nu"])) < 1e-8
+    smp.close(); eng.close()

@@ -179,3 +179,65 @@ def test_block_draws_from_sufficient_statistics(name, beta):
         expect = 1.0 / ((1.0 / ((beta / 2) * 3.25 + 1.0)) * 41.5)
     assert abs(smp.get()["sigma_sq"] - expect) < 1e-14
     smp.close()
+
+
+def _ragged_stats(s, d, bw=4):
+    """Pair cross-Gram band and B'Y'W of a ragged data set, computed per function with NumPy."""
+    W = _features(s, d)
+    q, P, n = W.shape[1], d.P, d.n
+    off = s["off"]
+    npairs = q * (q + 1) // 2
+    Hb = np.zeros((npairs, bw * P)); BtYW = np.zeros((P, q))
+    for i in range(n):
+        Bi = s["B"][off[i]:off[i + 1]]; yi = s["y"][off[i]:off[i + 1]]
+        Gi = Bi.T @ Bi
+        band = np.zeros(bw * P)
+        for j in range(bw):
+            for p in range(j, P):
+                band[j * P + p] = Gi[p - j, p]
+        assert np.allclose(np.triu(Gi, bw), 0)             # cubic B-splines: bandwidth 4
+        pr = 0
+        for a in range(q):
+            for b in range(a, q):
+                Hb[pr] += W[i, a] * W[i, b] * band
+                pr += 1
+        BtYW += np.outer(Bi.T @ yi, W[i])
+    return W.T @ W, BtYW, Hb
+
+
+@pytest.mark.parametrize("name", ["F_ragged", "F_cov_ragged"])
+@pytest.mark.parametrize("beta", [1.0, 0.6])
+def test_block_draws_ragged_grids(name, beta):
+    """Ragged grids: the per-pair banded cross-Gram carries the reference's block semantics."""
+    s, d, st = cases.build(name)
+    dr = cases.draws(name, s)
+    WtW, BtYW, Hb = _ragged_stats(s, d)
+    K, P, M, D = d.K, d.P, d.M, d.D
+    Pm = orc.pmat_rw1(P)
+    par = s["par"]
+    smp = bf.Sampler(hyper=bf.default_hyper(True), n_total=d.n, Pmat=Pm, dims=(d.n, K, P, M, D, 0, 1, 4),
+                     sum_half_total=1.0, n_points_total=1.0)
+    delta = np.ones((K, M)); delta[:, 0] = dr["tilde_tau"][:, 0]
+    for m in range(1, M):
+        delta[:, m] = dr["tilde_tau"][:, m] / dr["tilde_tau"][:, m - 1]
+    smp.set(nu=par["nu"], Phi=par["Phi"], sigma_sq=par["sigma_sq"], tau=dr["tau"], gamma=dr["gamma"], delta=delta)
+    if D:
+        dxi = np.ones((K, M, D)); dxi[:, 0, :] = dr["tilde_tau_xi"][:, 0, :]
+        for m in range(1, M):
+            dxi[:, m, :] = dr["tilde_tau_xi"][:, m, :] / dr["tilde_tau_xi"][:, m - 1, :]
+        smp.set_cov(eta=par["eta"], xi=par["xi"], tau_eta=dr["tau_eta"], gamma_xi=dr["gamma_xi"], delta_xi=dxi)
+    smp.set_hband(Hb)
+    tol = 2e-9
+    smp.tape(dr["z_phi"].ravel(order="F")); smp.host_update("phi", WtW, BtYW, beta)
+    assert rel(smp.get()["Phi"], orc.update_phi(d, st, dr["gamma"], dr["tilde_tau"], dr["z_phi"], beta)) < tol
+    smp.set(Phi=par["Phi"])
+    smp.tape(dr["z_nu"].ravel(order="F")); smp.host_update("nu", WtW, BtYW, beta)
+    assert rel(smp.get()["nu"], orc.update_nu(d, st, dr["tau"], Pm, dr["z_nu"], beta)) < tol
+    smp.set(nu=par["nu"])
+    if D:
+        smp.tape(dr["z_eta"].ravel(order="F")); smp.host_update("eta", WtW, BtYW, beta)
+        assert rel(smp.get_cov()["eta"], orc.update_eta(d, st, dr["tau_eta"], Pm, dr["z_eta"], beta)) < tol
+        smp.set_cov(eta=par["eta"])
+        smp.tape(dr["z_xi"].ravel(order="F")); smp.host_update("xi", WtW, BtYW, beta)
+        assert rel(smp.get_cov()["xi"], orc.update_xi(d, st, dr["gamma_xi"], dr["tilde_tau_xi"], dr["z_xi"], beta)) < tol
+    smp.close()
