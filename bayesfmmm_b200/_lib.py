@@ -32,7 +32,7 @@ EXPORTS = [
     "bfmmm_sampler_set", "bfmmm_sampler_get", "bfmmm_sampler_set_cov", "bfmmm_sampler_get_cov",
     "bfmmm_sampler_step", "bfmmm_sampler_run", "bfmmm_sampler_iteration", "bfmmm_sampler_last_accept",
     "bfmmm_sampler_tape", "bfmmm_sampler_tape_left", "bfmmm_sampler_tempered_transition",
-    "bfmmm_sampler_run_mtt", "bfmmm_sampler_tt_trace", "bfmmm_sampler_record", "bfmmm_sampler_batches_written",
+    "bfmmm_sampler_run_mtt", "bfmmm_sampler_tt_trace", "bfmmm_sampler_record", "bfmmm_sampler_batches_written", "bfmmm_sampler_profile",
     # include/bfmmm_io.h
     "bfmmm_save_mat_txt", "bfmmm_save_cube_txt", "bfmmm_save_field_cube_bin", "bfmmm_file_info", "bfmmm_load", "bfmmm_state_snapshot", "bfmmm_state_restore",
     "bfmmm_host_update_pi", "bfmmm_host_update_alpha3", "bfmmm_host_update_tau", "bfmmm_host_update_delta",

@@ -21,6 +21,7 @@ constexpr int RED_MAX = 8;      // values reduced per block in the per-function 
 
 struct PassArgs {
   int n, ld, P, D, QS;
+  int sm_count, max_blocks;         // launch geometry: persistent grid of at most max_blocks blocks
   const double* __restrict__ Ct;    // common basis: whitened c~ ; ragged grids: least-squares c_i
   const double* __restrict__ Gl;    // ragged grids: lower band of G_i, row (j*P + p) = G_i[p-j][p]; else nullptr
   int bw;                           // ragged grids: band width (degree + 1)
@@ -83,52 +84,134 @@ __host__ __device__ BF_NOINLINE inline double nl_log(double x) { return log(x); 
 __host__ __device__ BF_NOINLINE inline double nl_lgamma(double x) { return lgamma(x); }
 __host__ __device__ BF_NOINLINE inline double nl_pow(double x, double y) { return pow(x, y); }
 
+// log(1 + t) for small |t| by its Taylor series (|t| <= 0.05: truncation < 5e-16), else the library log
+__host__ __device__ inline double log1p_small(double t) {
+  if (fabs(t) > 0.05) return nl_log(1.0 + t);
+  double s = -1.0 / 10.0;
+  s = fma(s, t, 1.0 / 9.0);  s = fma(s, t, -1.0 / 8.0); s = fma(s, t, 1.0 / 7.0);  s = fma(s, t, -1.0 / 6.0);
+  s = fma(s, t, 1.0 / 5.0);  s = fma(s, t, -1.0 / 4.0); s = fma(s, t, 1.0 / 3.0);  s = fma(s, t, -1.0 / 2.0);
+  s = fma(s, t, 1.0);
+  return s * t;
+}
+
+// Counter-based random stream (generic path: host-side global draws, and the rare per-function cases
+// the kernels' straight-line fast paths hand over).  One Philox4x32-10 block yields four 32-bit words,
+// handed out word by word: a 53-bit uniform takes two words, a 32-bit one a single word.
 struct RngStream {
   uint32_t c0, c1, c2, ctr, k0, k1;
-  double spare; int have;
+  uint32_t w[4];
+  int nw;            // words left in w (taken from the top)
+  double nspare; int nhave;
   __host__ __device__ RngStream(uint64_t key, uint64_t index, uint64_t iteration, uint32_t purpose)
       : c0((uint32_t)index), c1((uint32_t)(index >> 32)), c2((uint32_t)(iteration * 64 + purpose)), ctr(0),
-        k0((uint32_t)key), k1((uint32_t)(key >> 32)), spare(0), have(0) {}
-  __host__ __device__ BF_NOINLINE double refill() {   // one Philox block -> two 53-bit uniforms
+        k0((uint32_t)key), k1((uint32_t)(key >> 32)), nw(0), nspare(0), nhave(0) { w[0] = w[1] = w[2] = w[3] = 0; }
+  __host__ __device__ BF_NOINLINE void refill() {
     uint32_t c[4] = {c0, c1, c2, ctr++};
     Philox::block(c, k0, k1);
-    uint64_t a = ((uint64_t)c[0] << 32) | c[1], b = ((uint64_t)c[2] << 32) | c[3];
-    spare = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    have = 1;
-    return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    w[0] = c[0]; w[1] = c[1]; w[2] = c[2]; w[3] = c[3];
+    nw = 4;
+  }
+  __host__ __device__ inline uint32_t word() {
+    if (nw == 0) refill();
+    nw--;
+    return nw == 3 ? w[3] : (nw == 2 ? w[2] : (nw == 1 ? w[1] : w[0]));
   }
   __host__ __device__ inline double uniform() {     // (0,1), 53 bits
-    if (have) { have = 0; return spare; }
-    return refill();
+    uint64_t a = ((uint64_t)word() << 32) | word();
+    return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   }
-  __host__ __device__ BF_NOINLINE double normal() {      // Box-Muller, one value per two uniforms
-    double u1 = uniform(), u2 = uniform();
+  __host__ __device__ inline double uniform32() {   // (0,1), 32 bits
+    return ((double)word() + 0.5) * (1.0 / 4294967296.0);
+  }
+  __host__ __device__ BF_NOINLINE double normal() {  // Box-Muller; both outputs are used
+    if (nhave) { nhave = 0; return nspare; }
+    double u1 = uniform(), u2 = uniform32();
     double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
 #ifdef __CUDA_ARCH__
-    return r * cospi(2.0 * u2);
+    sincospi(2.0 * u2, &sn, &cs);
 #else
-    return r * cos(6.283185307179586476925286766559 * u2);
+    sn = sin(6.283185307179586476925286766559 * u2); cs = cos(6.283185307179586476925286766559 * u2);
 #endif
+    nspare = r * sn; nhave = 1;
+    return r * cs;
   }
-  // Marsaglia-Tsang; shape < 1 boosted by U^(1/shape)
-  __host__ __device__ BF_NOINLINE double gamma(double shape) {
-    double boost = 1.0;
-    if (shape < 1.0) { boost = nl_pow(uniform(), 1.0 / shape); shape += 1.0; }
-    double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
-    for (int it = 0; it < 64; it++) {
-      double x = normal();
-      double v = 1.0 + c * x;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      double uu = uniform();
-      double x2 = x * x;
-      if (uu < 1.0 - 0.0331 * x2 * x2) return boost * d * v;
-      if (nl_log(uu) < 0.5 * x2 + d * (1.0 - v + nl_log(v))) return boost * d * v;
+  // Marsaglia-Tsang (2000); shape < 1 boosted by U^(1/shape).  The acceptance test
+  //   log U < x^2/2 + d (1 - v + log v) =: R
+  // is decided without a logarithm whenever U - 1 < R (accept, since log U <= U - 1) or
+  // 1 - 1/U >= R (reject, since log U >= 1 - 1/U); log v = 3 log1p(c x) by its series.
+  // If log_out != nullptr it receives log of the returned variate.
+  __host__ __device__ BF_NOINLINE double gamma(double shape, double* log_out = nullptr) {
+    double boost = 1.0, lboost = 0.0;
+    if (shape < 1.0) {
+      lboost = nl_log(uniform()) / shape; boost = exp(lboost);
+      shape += 1.0;
     }
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 64; it++) {
+      const double x = normal();
+      const double t = c * x;
+      if (t <= -1.0) continue;
+      const double v1 = 1.0 + t;
+      const double v = v1 * v1 * v1;
+      const double l3 = 3.0 * log1p_small(t);
+      const double uu = uniform();
+      const double R = 0.5 * x * x + d * (1.0 - v + l3);
+      bool ok;
+      if (uu - 1.0 < R) ok = true;
+      else if (1.0 - 1.0 / uu >= R) ok = false;
+      else ok = nl_log(uu) < R;
+      if (ok) {
+        if (log_out) *log_out = nl_log(d) + l3 + lboost;
+        return boost * d * v;
+      }
+    }
+    if (log_out) *log_out = nl_log(boost * d);
     return boost * d;   // unreachable in practice (acceptance > 95% per trial)
   }
 };
-enum { RNG_Z_PROPOSAL = 1, RNG_Z_ACCEPT = 2, RNG_CHI = 3 };
+
+// ---- straight-line device fast paths (no loops, no calls: every lane of a warp does the same work) ----
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox_words(uint64_t key, uint64_t index, uint64_t iteration, uint32_t purpose,
+                                             uint32_t block, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), (uint32_t)(iteration * 64 + purpose), block};
+  Philox::block(c, (uint32_t)key, (uint32_t)(key >> 32));
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  uint64_t a = ((uint64_t)hi << 32) | lo;
+  return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double u32(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+// two independent standard normals from three words (53-bit radius uniform, 32-bit angle)
+__device__ __forceinline__ void box_muller_pair(uint32_t w0, uint32_t w1, uint32_t w2, double& n0, double& n1) {
+  const double r = sqrt(-2.0 * log(u53(w0, w1)));
+  double sn, cs;
+  sincospi(2.0 * u32(w2), &sn, &cs);
+  n0 = r * cs; n1 = r * sn;
+}
+// One Marsaglia-Tsang candidate for shape >= 1 from a given normal and accept-uniform; returns false
+// only if the candidate is truly rejected (probability ~1e-3 at shape 10, ~1e-5 at shape 3000; the
+// caller then falls back to RngStream::gamma).  The logarithm of the accept-uniform is evaluated only
+// by the lanes the log-free bound U - 1 < R does not already accept.
+// log_shape = log(shape) is supplied by the caller; lg receives log of the variate.
+__device__ __forceinline__ bool gamma_candidate(double shape, double log_shape, double x, double uu, double& g, double& lg) {
+  const double d = shape - 1.0 / 3.0;
+  const double c = rsqrt(9.0 * d);
+  const double t = c * x;
+  const double v1 = 1.0 + t;
+  const double v = v1 * v1 * v1;
+  const double l3 = 3.0 * log1p_small(t > -0.99 ? t : -0.99);
+  const double R = 0.5 * x * x + d * (1.0 - v + l3);
+  g = d * v;
+  lg = log_shape + log1p_small(-1.0 / (3.0 * shape)) + l3;
+  bool ok = (uu - 1.0 < R);
+  if (!ok) ok = nl_log(uu) < R;
+  return ok && (t > -0.99);
+}
+#endif
+enum { RNG_Z_PROPOSAL = 1, RNG_Z_ACCEPT = 2, RNG_CHI = 3, RNG_Z_PROPOSAL_SLOW = 4 };
 
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }

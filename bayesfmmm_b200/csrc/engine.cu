@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -295,7 +296,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q;
   if (e->ragged) e->stats_len += (int64_t)(e->q * (e->q + 1) / 2) * bf::BWMAX * e->P;   // upper bound (bw <= BWMAX)
   CUE(cudaMalloc(&e->stats, e->stats_len * 8));
-  e->pass_blocks = bf::pass_grid(e->ld, 1);
+  e->pass_blocks = std::min(bf::pass_grid(e->ld, 1), e->sm_count * 16);
   CUE(cudaMalloc(&e->partials, (size_t)e->pass_blocks * bf::RED_MAX * 8));
   e->st_blocks = bf::stats_blocks(e->sm_count);
   CUE(cudaMalloc(&e->st_partials, bf::stats_partial_doubles(e->P, e->q, e->st_blocks) * 8));
@@ -426,6 +427,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
 static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
   a.n = e->n; a.ld = e->ld; a.P = e->P; a.D = e->D; a.QS = e->QS;
+  a.sm_count = e->sm_count; a.max_blocks = e->pass_blocks;
   a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
   a.sigma_sq = e->sigma_sq; a.beta = beta;
   a.key = e->key; a.iteration = e->iteration; a.global_offset = (uint64_t)e->global_offset;
@@ -438,6 +440,10 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
   fill_pass(e, a, beta);
   a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM);
   for (int k = 0; k < e->K; k++) a.pi[k] = pi[k];
+#ifdef BF_TUNE_V
+  static const bool force_inject = std::getenv("BFMMM_Z_INJECT") != nullptr;   // tuning: time the step without the RNG
+  injected = injected || force_inject;
+#endif
   if (injected) { a.gam = e->draws; a.u = e->draws + (size_t)e->K * e->ld; }
   if (dump_draws) a.draws_out = e->draws;
   a.acc_out = e->acc_dbg;

@@ -4,7 +4,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -118,6 +121,91 @@ void pinv_sym_jacobi(int n, const double* A, double* Ainv) {
   }
 }
 
+// ---- contiguous-inner-loop variants used by the per-sweep block draws (P x P, P ~ 20..400) ----
+// Cholesky factor of a symmetric matrix, ROW-major lower triangle (row i = L[i*n .. i*n+i])
+bool chol_rows(int n, const double* A, double* L) {
+  for (int i = 0; i < n; i++) {
+    double* li = L + (size_t)i * n;
+    for (int j = 0; j <= i; j++) {
+      const double* lj = L + (size_t)j * n;
+      double s = A[(size_t)j * n + i];
+      for (int k = 0; k < j; k++) s -= li[k] * lj[k];
+      if (j == i) {
+        if (!(s > 0)) return false;
+        li[i] = std::sqrt(s);
+      } else {
+        li[j] = s / lj[j];
+      }
+    }
+    for (int j = i + 1; j < n; j++) li[j] = 0.0;
+  }
+  return true;
+}
+// C = (L L')^{-1} from the row-major factor: columns of L^{-1} by forward substitution (stored
+// column-major in W, column j occupies W[j*n + j .. j*n + n-1]), then C[i][j] = sum_{k >= max(i,j)} W_ki W_kj
+void inv_from_chol_rows(int n, const double* L, double* C, double* W) {
+  for (int j = 0; j < n; j++) {
+    double* x = W + (size_t)j * n;
+    for (int i = 0; i < j; i++) x[i] = 0.0;
+    for (int i = j; i < n; i++) {
+      const double* li = L + (size_t)i * n;
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int k = j; k < i; k++) s -= li[k] * x[k];
+      x[i] = s / li[i];
+    }
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      const double* xi = W + (size_t)i * n;
+      const double* xj = W + (size_t)j * n;
+      double s = 0;
+      for (int k = i; k < n; k++) s += xi[k] * xj[k];
+      C[(size_t)j * n + i] = s;
+      C[(size_t)i * n + j] = s;
+    }
+}
+
+// "Reverse" Cholesky A = U U' with U UPPER triangular, row-major (row i = U[i*n + i .. i*n + n-1]).
+// Why: the reference draws  x = C b + chol_lower(C) z  with C = A^{-1} (UpdateNu.h:67-69, UpdatePhi.h:79-82).
+// With A = U U',  C = U^{-T} U^{-1} = (U^{-T})(U^{-T})' and U^{-T} is lower triangular with positive
+// diagonal, so by uniqueness chol_lower(C) = U^{-T} and
+//     x = U^{-T} (U^{-1} b + z):
+// one factorisation and two triangular solves give the reference's map exactly -- no explicit
+// inverse and no second factorisation (5x fewer flops than inv + chol).
+bool chol_upper_rev(int n, const double* A, double* U) {
+  for (int j = n - 1; j >= 0; j--) {
+    double* uj = U + (size_t)j * n;
+    double s = A[(size_t)j * n + j];
+    for (int k = j + 1; k < n; k++) s -= uj[k] * uj[k];
+    if (!(s > 0)) return false;
+    const double d = std::sqrt(s);
+    uj[j] = d;
+    for (int i = 0; i < j; i++) {
+      double* ui = U + (size_t)i * n;
+      double t = A[(size_t)j * n + i];
+      for (int k = j + 1; k < n; k++) t -= ui[k] * uj[k];
+      ui[j] = t / d;
+    }
+  }
+  return true;
+}
+// x = U^{-T} (U^{-1} b + z)
+void draw_from_rev_chol(int n, const double* U, const double* b, const double* z, double* x, double* w) {
+  for (int i = n - 1; i >= 0; i--) {                 // U w = b
+    const double* ui = U + (size_t)i * n;
+    double s = b[i];
+    for (int k = i + 1; k < n; k++) s -= ui[k] * w[k];
+    w[i] = s / ui[i];
+  }
+  for (int i = 0; i < n; i++) w[i] += z[i];
+  for (int k = 0; k < n; k++) {                      // U' x = w  (column-oriented forward substitution)
+    const double* uk = U + (size_t)k * n;
+    const double xk = w[k] / uk[k];
+    x[k] = xk;
+    for (int i = k + 1; i < n; i++) w[i] -= uk[i] * xk;
+  }
+}
+
 double lgamma_d(double x) { return std::lgamma(x); }
 double pnorm_std(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
 double qnorm_std(double p) {          // Acklam's rational approximation + Halley refinement
@@ -185,6 +273,9 @@ struct bfmmm_sampler {
   vecd tt_ssr, tt_sigma;   // per-slot trace of the last tempered transition
   double last_ssr = 0;     // SSR of the state the last sweep ended with
   int64_t tt_accepts = 0, tt_total = 0;
+  // wall-clock split of the sweeps run so far (seconds): host draws | waiting for the device (launch,
+  // all-reduce, read-back) | pushing globals
+  double t_host = 0, t_wait = 0, t_push = 0;
   // stored-sample recorder (BFMMM.h:1680-1746)
   struct Recorder {
     bool on = false;
@@ -297,21 +388,29 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
       s->Prec[(size_t)c * P + r] = sc * saa * g + pr;
     }
   }
-  if (!inv_spd(P, s->Prec.data(), s->C.data(), s->work)) {
+  s->work.resize((size_t)2 * P * P);
+  for (int p = 0; p < P; p++) s->v2[p] = s->rng.normal();
+  double* U = s->work.data();
+  if (chol_upper_rev(P, s->Prec.data(), U)) {
+    draw_from_rev_chol(P, U, s->rhs.data(), s->v2.data(), s->v1.data(), s->work.data() + (size_t)P * P);
+  } else {
+    // singular precision: Moore-Penrose inverse, symmetrised, then mean + chol_lower(C) z as written
+    // in the reference (UpdateNu.h:67-69)
     pinv_sym_jacobi(P, s->Prec.data(), s->C.data());
     for (int c = 0; c < P; c++)
       for (int r = c + 1; r < P; r++) {
         double t = (s->C[(size_t)c * P + r] + s->C[(size_t)r * P + c]) / 2;
         s->C[(size_t)c * P + r] = t; s->C[(size_t)r * P + c] = t;
       }
-  }
-  if (!chol_lower(P, s->C.data(), s->Lc.data())) return sfail("block draw: covariance is not positive definite");
-  for (int p = 0; p < P; p++) s->v2[p] = s->rng.normal();
-  for (int r = 0; r < P; r++) {
-    double mean = 0, dev = 0;
-    for (int c = 0; c < P; c++) mean += s->C[(size_t)c * P + r] * s->rhs[c];
-    for (int c = 0; c <= r; c++) dev += s->Lc[(size_t)c * P + r] * s->v2[c];
-    s->v1[r] = mean + dev;
+    if (!chol_rows(P, s->C.data(), s->Lc.data())) return sfail("block draw: covariance is not positive definite");
+    for (int r = 0; r < P; r++) {
+      const double* cr = s->C.data() + (size_t)r * P;      // symmetric: row r == column r
+      const double* lr = s->Lc.data() + (size_t)r * P;
+      double mean = 0, dev = 0;
+      for (int c = 0; c < P; c++) mean += cr[c] * s->rhs[c];
+      for (int c = 0; c <= r; c++) dev += lr[c] * s->v2[c];
+      s->v1[r] = mean + dev;
+    }
   }
   set_coef(s, k, mm, dd, s->v1.data());
   return 0;
@@ -323,12 +422,17 @@ double calc_lB(const double* al, int K) {
   return lB - lgamma_d(tot);
 }
 
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 int push_globals(bfmmm_sampler* s) {
+  struct T { bfmmm_sampler* s; double t0; ~T() { s->t_push += now_s() - t0; } } timer{s, now_s()};
   return bfmmm_set_globals(s->e, s->nu.data(), s->Phi.data(), s->D ? s->eta.data() : nullptr,
                            s->D ? s->xi.data() : nullptr, s->sigma_sq);
 }
 
 int reduce_and_read(bfmmm_sampler* s) {
+  struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
   double* dev = nullptr; int64_t len = 0;
   if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
   if (s->allreduce) {
@@ -863,9 +967,22 @@ static int record_iteration(bfmmm_sampler* s) {
 }
 
 // ================================================================= driver loops
+static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta);
 int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   if (!s) return sfail("null sampler");
   if (!s->e) return sfail("bfmmm_sampler_step: detached sampler has no engine");
+  const double t0 = now_s(), w0 = s->t_wait, p0 = s->t_push;
+  int rc = sampler_step_impl(s, sweep, beta);
+  s->t_host += (now_s() - t0) - (s->t_wait - w0) - (s->t_push - p0);
+  return rc;
+}
+// seconds spent so far in: host-side draws | waiting on the device | pushing globals
+int bfmmm_sampler_profile(bfmmm_sampler* s, double* out3) {
+  if (!s) return sfail("null sampler");
+  out3[0] = s->t_host; out3[1] = s->t_wait; out3[2] = s->t_push;
+  return 0;
+}
+static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   bfmmm_engine* e = s->e;
   s->rng.iteration = (uint64_t)s->tick;
   const bool do_z = (sweep == BFMMM_SWEEP_NU_Z || sweep == BFMMM_SWEEP_FULL);
@@ -882,22 +999,27 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   if (bfmmm_suffstats_async(e)) return 1;
   if (reduce_and_read(s)) return 1;
   if (s->ragged) s->Hb = st_hb(s);
-  if (do_z) {
-    s->last_accept = (int64_t)std::llround(st_acc(s));
+  if (do_z) s->last_accept = (int64_t)std::llround(st_acc(s));
+  // The Gaussian blocks that change the mean (Phi, nu) are drawn first so that the SSR pass can start;
+  // the prior updates that do not feed this sweep's device passes (pi, alpha_3, delta, A, gamma, tau)
+  // then run on the host WHILE the device streams the SSR pass.  Each update draws from its own
+  // Philox stream and reads exactly what it reads in the reference's order (Phi uses the previous
+  // delta/gamma, nu the previous tau; delta, A, gamma see the new Phi; tau the new nu), so the chain is
+  // the one of BFMMM.h:1500-1554 -- only wall-clock placement differs.
+  if (do_phi && bfmmm_host_update_phi(s, st_wtw(s), st_btyw(s), beta)) return 1;   // updatePhi
+  if (do_nu && bfmmm_host_update_nu(s, st_wtw(s), st_btyw(s), beta)) return 1;     // updateNu
+  if (push_globals(s)) return 1;
+  if (bfmmm_ssr_async(e)) return 1;                        // updateSigma's data pass, new globals
+  if (do_z) {                                              // updatePi_PM -> updateAlpha3
     if (bfmmm_host_update_pi(s, st_slz(s))) return 1;
     if (bfmmm_host_update_alpha3(s, st_slz(s))) return 1;
   }
-  if (do_phi) {                                            // updatePhi, updateDelta, updateA, updateGamma
-    if (bfmmm_host_update_phi(s, st_wtw(s), st_btyw(s), beta)) return 1;
+  if (do_phi) {                                            // updateDelta, updateA, updateGamma
     if (bfmmm_host_update_delta(s)) return 1;
     if (bfmmm_host_update_A(s)) return 1;
     if (bfmmm_host_update_gamma(s)) return 1;
   }
-  if (do_nu && bfmmm_host_update_nu(s, st_wtw(s), st_btyw(s), beta)) return 1;     // updateNu
   if (bfmmm_host_update_tau(s)) return 1;                  // updateTau (all three loops call it)
-  // updateSigma: data pass with the new globals
-  if (push_globals(s)) return 1;
-  if (bfmmm_ssr_async(e)) return 1;
   if (reduce_and_read(s)) return 1;
   if (bfmmm_host_update_sigma(s, st_ssr(s), beta, tempered)) return 1;
   double ssr_ll = st_ssr(s);
@@ -992,6 +1114,7 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
     HostRng rng = s->rng;
     *s = saved;
     s->tt_ssr = tssr; s->tt_sigma = tsig; s->tick = tk; s->tt_accepts = acc; s->tt_total = tot; s->rng = rng;
+    if (s->ragged) s->Hb = st_hb(s);
     if (bfmmm_state_restore(s->e)) return 1;
   }
   if (s->rec.on && record_iteration(s)) return 1;

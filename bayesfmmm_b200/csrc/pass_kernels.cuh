@@ -4,6 +4,9 @@
 // warp reads 512 contiguous bytes per row.  The global coefficients live in shared memory
 // (broadcast reads).  K and M are compile-time so all per-function state stays in registers.
 #pragma once
+#include <unordered_map>
+#include <utility>
+
 #include "common.cuh"
 
 namespace bf {
@@ -216,14 +219,18 @@ template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
-  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
   double red[K + 1];
 #pragma unroll
   for (int j = 0; j <= K; j++) red[j] = 0;
-  if (i0 < a.ld) {
+  // persistent blocks: every thread walks the functions with a grid stride, one reduction per block
+  for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);
-    double zp[V][K], uacc[V];
+    double zp[V][K], uacc[V], lzo[V][K], lzn[V][K];
+#pragma unroll
+    for (int v = 0; v < V; v++)
+#pragma unroll
+      for (int k = 0; k < K; k++) lzo[v][k] = nl_log(st.z[v][k]);
     // ---- proposal
     if (a.gam) {
       double t[V];
@@ -234,36 +241,83 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
         for (int v = 0; v < V; v++) zp[v][k] = t[v];
       }
       ldv_cs<V>(a.u + i0, uacc);
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        double sum = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) sum += zp[v][k];
+#pragma unroll
+        for (int k = 0; k < K; k++) { zp[v][k] = zp[v][k] / sum; lzn[v][k] = nl_log(zp[v][k]); }
+      }
     } else {
 #pragma unroll
       for (int v = 0; v < V; v++) {
-        RngStream rs(a.key, a.global_offset + (uint64_t)(i0 + v), a.iteration, RNG_Z_PROPOSAL);
+        const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
+        double lg[K], sum = 0;
+        bool fast = (K <= 4) && (i0 + v < a.n);
+        bool small = false;
+        double sh[K], lsh[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-          double sh = a.a_Z_PM * st.z[v][k];
-          if (sh <= 0) sh = 10;                    // Distributions.h:24-28
-          zp[v][k] = (i0 + v < a.n) ? rs.gamma(sh) : 1.0;
+          sh[k] = a.a_Z_PM * st.z[v][k]; lsh[k] = a.log_a_Z_PM + lzo[v][k];
+          if (sh[k] <= 0) { sh[k] = 10; lsh[k] = 2.302585092994045684; }   // Distributions.h:24-28
+          small = small || (sh[k] < 1.0);
         }
-        uacc[v] = rs.uniform();
-      }
-      if (a.draws_out) {
-        double t[V];
+        if constexpr (K <= 4) {
+          // straight-line path: three Philox blocks give two Box-Muller pairs (4 normals), four 32-bit
+          // accept uniforms and the 53-bit Metropolis uniform; one Marsaglia-Tsang candidate per coordinate
+          uint32_t w0[4], w1[4], w2[4];
+          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 0, w0);
+          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 1, w1);
+          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 2, w2);
+          double nrm[4];
+          box_muller_pair(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
+          box_muller_pair(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
+          const double ua[4] = {u32(w0[3]), u32(w1[3]), u32(w2[2]), u32(w2[3])};
+          uacc[v] = u53(w2[0], w2[1]);
+          // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are
+          // only generated by warps that contain such a function
+          double ub[4] = {0.5, 0.5, 0.5, 0.5};
+          if (__any_sync(__activemask(), small)) {
+            uint32_t w3[4], w4[4];
+            philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 3, w3);
+            philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 4, w4);
+            ub[0] = u53(w3[0], w3[1]); ub[1] = u53(w3[2], w3[3]); ub[2] = u53(w4[0], w4[1]); ub[3] = u53(w4[2], w4[3]);
+          }
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-#pragma unroll
-          for (int v = 0; v < V; v++) t[v] = zp[v][k];
-          stv<V>(a.draws_out + (size_t)k * a.ld + i0, t);
+          for (int k = 0; k < K; k++) {
+            const bool bo = sh[k] < 1.0;
+            const double she = bo ? sh[k] + 1.0 : sh[k];
+            const double lshe = bo ? log1p_small(sh[k]) : lsh[k];
+            const bool ok = gamma_candidate(she, lshe, nrm[k], ua[k], zp[v][k], lg[k]);
+            if (bo) {
+              const double lb = nl_log(ub[k]) / sh[k];
+              zp[v][k] *= exp(lb); lg[k] += lb;
+            }
+            fast = fast && ok;
+          }
         }
-        stv<V>(a.draws_out + (size_t)K * a.ld + i0, uacc);
+        if (!fast) {          // a rejected candidate, K > 4 or padding: generic sampler
+          RngStream rs(a.key, gi, a.iteration, RNG_Z_PROPOSAL_SLOW);
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            if (i0 + v < a.n) zp[v][k] = rs.gamma(sh[k], &lg[k]);
+            else { zp[v][k] = 1.0; lg[k] = 0.0; }
+          }
+          if (K > 4) uacc[v] = rs.uniform();
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) sum += zp[v][k];
+        if (a.draws_out) {
+#pragma unroll
+          for (int k = 0; k < K; k++) a.draws_out[(size_t)k * a.ld + i0 + v] = zp[v][k];
+          a.draws_out[(size_t)K * a.ld + i0 + v] = uacc[v];
+        }
+        // log of the normalised proposal from the sampler's own log (one library log instead of K)
+        const double lsum = nl_log(sum);
+#pragma unroll
+        for (int k = 0; k < K; k++) { zp[v][k] = zp[v][k] / sum; lzn[v][k] = lg[k] - lsum; }
       }
-    }
-#pragma unroll
-    for (int v = 0; v < V; v++) {
-      double sum = 0;
-#pragma unroll
-      for (int k = 0; k < K; k++) sum += zp[v][k];
-#pragma unroll
-      for (int k = 0; k < K; k++) zp[v][k] = zp[v][k] / sum;
     }
     // ---- squared errors of the current and the proposed state
     double so[V], sn[V];
@@ -305,15 +359,12 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
     double znew[V][K];
 #pragma unroll
     for (int v = 0; v < V; v++) {
-      double lzo[K], lzn[K];
       double lp_old = 0, lp_new = 0;
       bool nonpos = false;
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        lzo[k] = nl_log(st.z[v][k]);
-        lzn[k] = nl_log(zp[v][k]);
-        lp_old += (a.alpha3 * a.pi[k] - 1) * lzo[k];
-        lp_new += (a.alpha3 * a.pi[k] - 1) * lzn[k];
+        lp_old += (a.alpha3 * a.pi[k] - 1) * lzo[v][k];
+        lp_new += (a.alpha3 * a.pi[k] - 1) * lzn[v][k];
         nonpos |= (st.z[v][k] <= 0);
       }
       lp_old -= a.beta * (so[v] / (2 * a.sigma_sq));
@@ -323,14 +374,15 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
       for (int k = 0; k < K; k++) {
         double al_from_old = a.a_Z_PM * st.z[v][k];   // parameters used to propose the new state
         double al_from_new = a.a_Z_PM * zp[v][k];     // parameters of the reverse move
-        q_new += (al_from_old - 1) * lzn[k];
-        q_old += (al_from_new - 1) * lzo[k];
+        q_new += (al_from_old - 1) * lzn[v][k];
+        q_old += (al_from_new - 1) * lzo[v][k];
         // log(a * z) = log a + log z: both logs are already in registers
-        lB_new += lgamma_known_log(al_from_old, a.log_a_Z_PM + lzo[k]); tot_new += al_from_old;
-        lB_old += lgamma_known_log(al_from_new, a.log_a_Z_PM + lzn[k]); tot_old += al_from_new;
+        lB_new += lgamma_known_log(al_from_old, a.log_a_Z_PM + lzo[v][k]); tot_new += al_from_old;
+        lB_old += lgamma_known_log(al_from_new, a.log_a_Z_PM + lzn[v][k]); tot_old += al_from_new;
       }
-      q_new -= (lB_new - lgamma_known_log(tot_new, nl_log(tot_new)));
-      q_old -= (lB_old - lgamma_known_log(tot_old, nl_log(tot_old)));
+      // tot = a * sum_k z_k with sum_k z_k = 1 up to rounding: log(tot) = log a + log1p(tot/a - 1)
+      q_new -= (lB_new - lgamma_known_log(tot_new, a.log_a_Z_PM + log1p_small((tot_new - a.a_Z_PM) / a.a_Z_PM)));
+      q_old -= (lB_old - lgamma_known_log(tot_old, a.log_a_Z_PM + log1p_small((tot_old - a.a_Z_PM) / a.a_Z_PM)));
       double acc = lp_new - lp_old + q_old - q_new;
       if (nonpos) acc = 1;                           // UpdateMixedMembership.h:170-174
       const bool live = (i0 + v) < a.n;
@@ -339,7 +391,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
 #pragma unroll
       for (int k = 0; k < K; k++) {
         znew[v][k] = take ? zp[v][k] : st.z[v][k];
-        if (live) red[k] += take ? lzn[k] : lzo[k];
+        if (live) red[k] += take ? lzn[v][k] : lzo[v][k];
       }
       if (take) red[K] += 1.0;
     }
@@ -365,9 +417,8 @@ template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
-  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
   double red[1] = {0};
-  if (i0 < a.ld) {
+  for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);
     double G[V][M][M], r[V][M], d0[V];
@@ -442,9 +493,17 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
     } else {
 #pragma unroll
       for (int v = 0; v < V; v++) {
-        RngStream rs(a.key, a.global_offset + (uint64_t)(i0 + v), a.iteration, RNG_CHI);
+        // (M+1)/2 Box-Muller pairs, one Philox block each (three words used)
+        const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
 #pragma unroll
-        for (int m = 0; m < M; m++) eps[v][m] = rs.normal();
+        for (int pr = 0; pr < (M + 1) / 2; pr++) {
+          uint32_t w[4];
+          philox_words(a.key, gi, a.iteration, RNG_CHI, pr, w);
+          double n0, n1;
+          box_muller_pair(w[0], w[1], w[2], n0, n1);
+          eps[v][2 * pr] = n0;
+          if (2 * pr + 1 < M) eps[v][2 * pr + 1] = n1;
+        }
       }
       if (a.draws_out) {
         double t[V];
@@ -501,9 +560,8 @@ template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
   extern __shared__ double g[];
   stage_globals(a, g);
-  const int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V;
   double red[1] = {0};
-  if (i0 < a.ld) {
+  for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);
     double acc[V];
@@ -560,11 +618,25 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
 template <int V, typename Kern>
 inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s) {
   size_t smem = (size_t)a.P * a.QS * sizeof(double);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  // resident blocks per SM of this instantiation (queried once), grid = one full wave
+  static std::unordered_map<const void*, std::pair<size_t, int>> cache;   // kernel -> (smem, blocks per SM)
+  auto it = cache.find((const void*)kern);
+  if (it == cache.end() || it->second.first != smem) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PF_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+    cache[(const void*)kern] = std::make_pair(smem, nb);
+    it = cache.find((const void*)kern);
   }
-  kern<<<pass_grid(a.ld, V), PF_THREADS, smem, s>>>(a);
+  const int per_sm = it->second.second;
+  int need = pass_grid(a.ld, V);
+  int grid = a.sm_count * per_sm;
+  if (grid > need) grid = need;
+  if (grid > a.max_blocks) grid = a.max_blocks;
+  kern<<<grid, PF_THREADS, smem, s>>>(a);
   g_launch_count++;
   return (int)cudaGetLastError();
 }

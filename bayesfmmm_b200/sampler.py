@@ -152,6 +152,11 @@ class Sampler:
     def batches_written(self):
         return int(self._lib.bfmmm_sampler_batches_written(self._h))
 
+    def profile(self):
+        out = np.zeros(3)
+        self._chk(self._lib.bfmmm_sampler_profile(self._h, _p(out)))
+        return dict(host_s=out[0], wait_s=out[1], push_s=out[2])
+
     def tt_trace(self, N_t):
         n = 2 * N_t + 1
         ssr, sig = np.zeros(n), np.zeros(n)

@@ -30,8 +30,8 @@ UNIT = "Gibbs iterations/s (full warm-start sweep, n_funct=1M K=3 P=20 M=3 per G
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000, help="functions per GPU")
     ap.add_argument("--T", type=int, default=200)
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -244,12 +244,14 @@ def run_ours(a):
 
     # ---- headline: K sweeps with everything resident in HBM
     smp.run(bf.SWEEP_FULL, a.warmup)
+    prof0 = smp.profile()
     clocks = ClockSampler(local)
     clocks.start()
     l0 = eng.launch_count
     ms = timed(lambda k: smp.run(bf.SWEEP_FULL, k), a.steps)
     launches = eng.launch_count - l0
     clk = clocks.stop()
+    prof1 = smp.profile()
     value = world * a.steps / (ms * 1e-3)
 
     # ---- e2e: the same sweep through the host-buffer API, copying the new Z and chi back into the
@@ -309,6 +311,7 @@ def run_ours(a):
                       "timing": "inputs larger than L2 (216 MB projected cache + state per pass vs 126 MB L2)",
                       "rng": "device Philox (no injected draws)", "create_s_untimed": create_s},
            "clocks": clk, "gpu_launches": int(launches),
+           "host_split_ms_per_step": {k.replace("_s", ""): (prof1[k] - prof0[k]) / a.steps * 1e3 for k in prof1},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "steps": e_steps, "ms_per_step": ms_e / e_steps},
            "roofline": roofline}

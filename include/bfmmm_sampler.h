@@ -96,6 +96,8 @@ int bfmmm_sampler_record(bfmmm_sampler* s, const char* directory, int r_stored_i
 int bfmmm_sampler_batches_written(bfmmm_sampler* s);
 /* per-slot (SSR, sigma^2) of the last tempered transition, slots 0..2*N_t */
 int bfmmm_sampler_tt_trace(bfmmm_sampler* s, double* ssr, double* sigma, int n);
+/* wall-clock split of the sweeps so far, seconds: {host draws, waiting on the device, pushing globals} */
+int bfmmm_sampler_profile(bfmmm_sampler* s, double* out3);
 int64_t bfmmm_sampler_iteration(bfmmm_sampler* s);
 /* acceptance count of the last Z step (summed over shards) */
 int64_t bfmmm_sampler_last_accept(bfmmm_sampler* s);

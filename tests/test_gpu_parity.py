@@ -192,3 +192,35 @@ def test_ragged_sweep_matches_oracle_updates(name):
     smp.tape(dr["z_nu"].ravel(order="F")); smp.host_update("nu", WtW, BtYW, 1.0)
     assert rel(smp.get()["nu"], orc.update_nu(d, st, dr["tau"], orc.pmat_rw1(d.P), dr["z_nu"])) < 1e-8
     smp.close(); eng.close()
+
+
+def test_device_rng_distributions():
+    """The device generators (Philox4x32-10 + ziggurat normal + Marsaglia-Tsang gamma) have the right
+    laws: Kolmogorov-Smirnov against SciPy on 3e5 normals and on gammas of small, moderate and large
+    shape, plus the log of the gamma variate that the Z step reuses."""
+    import scipy.stats as sst
+    import bayesfmmm_b200 as bf
+    from bayesfmmm_b200.engine import MULTIVARIATE
+    n, K, M, P = 100_000, 3, 3, 4
+    rng = np.random.default_rng(0)
+    a_Z = 100.0
+    Z = np.empty((n, K)); Z[:, 0] = 0.004; Z[:, 1] = 0.03; Z[:, 2] = 1 - Z[:, 0] - Z[:, 1]   # shapes 0.4, 3, 96.6
+    eng = bf.Engine(model=MULTIVARIATE, n=n, K=K, P=P, M=M, y=rng.normal(size=(n, P)))
+    eng.set_state(Z, rng.normal(size=(n, M)))
+    eng.set_globals(rng.normal(size=(K, P)), 0.1 * rng.normal(size=(K, P, M)), 1.0)
+    eng.seed(99, 3)
+    eps = eng.debug_update_chi_rng()
+    x = eps.ravel()
+    assert sst.kstest(x, "norm").pvalue > 1e-3
+    assert abs(x.mean()) < 4 / np.sqrt(x.size) and abs(x.var() - 1) < 0.01
+    assert abs(sst.kurtosis(x)) < 0.05 and abs(sst.skew(x)) < 0.02
+    assert abs(np.mean(np.abs(x) > 3.5) / (2 * sst.norm.sf(3.5)) - 1) < 0.25       # the ziggurat tail
+    # independence across functions / coordinates
+    assert abs(np.corrcoef(eps[:, 0], eps[:, 1])[0, 1]) < 0.01 and abs(np.corrcoef(x[:-1], x[1:])[0, 1]) < 0.01
+    eng.set_state(Z, None)
+    gam, u = eng.debug_update_z_rng(np.ones(K) / K, 1.0, a_Z)
+    assert sst.kstest(u, "uniform").pvalue > 1e-3
+    for k in range(K):
+        shape = a_Z * Z[0, k]
+        assert sst.kstest(gam[:, k], "gamma", args=(shape,)).pvalue > 1e-3, (k, shape)
+    eng.close()
