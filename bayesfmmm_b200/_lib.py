@@ -33,6 +33,8 @@ EXPORTS = [
     "bfmmm_sampler_step", "bfmmm_sampler_run", "bfmmm_sampler_iteration", "bfmmm_sampler_last_accept",
     "bfmmm_sampler_tape", "bfmmm_sampler_tape_left", "bfmmm_sampler_tempered_transition",
     "bfmmm_sampler_run_mtt", "bfmmm_sampler_tt_trace", "bfmmm_sampler_record", "bfmmm_sampler_batches_written", "bfmmm_sampler_profile",
+    # include/bfmmm_basis.h
+    "bfmmm_bspline_basis", "bfmmm_tensor_bspline", "bfmmm_tensor_P", "bfmmm_get_P", "bfmmm_pmat_rw1",
     # include/bfmmm_io.h
     "bfmmm_save_mat_txt", "bfmmm_save_cube_txt", "bfmmm_save_field_cube_bin", "bfmmm_file_info", "bfmmm_load", "bfmmm_state_snapshot", "bfmmm_state_restore",
     "bfmmm_host_update_pi", "bfmmm_host_update_alpha3", "bfmmm_host_update_tau", "bfmmm_host_update_delta",

@@ -196,3 +196,56 @@ def test_ragged_covariate_adjusted_full_sweep():
     c = smp.get_cov()
     assert np.all(np.isfinite(c["eta"])) and np.all(np.isfinite(c["xi"])) and np.all(c["tau_eta"] > 0)
     smp.close(); eng.close()
+
+
+def test_high_dimensional_functional_matches_reference_stored_chain():
+    """BHDFMMM example of the reference (HDSim_data.RDS: 20 surfaces on a common 12 x 12 grid, K=2,
+    tensor basis degree (2,2), knots 250/500/750 -> P=36, M=2; UserFunctions.cpp:2456-2461): the
+    functional engine fed with bfmmm_tensor_bspline / bfmmm_get_P reproduces the posterior of sigma^2 of
+    the stored chain inst/test-data/HDFunctional_trace/Sigma0.txt (second-half median 0.00183)."""
+    from bayesfmmm_b200 import basis
+    G = np.load(os.path.join(GOLD, "sim_inputs.npz")); S = np.load(os.path.join(GOLD, "trace_summaries.npz"))
+    y, t = G["hd_y"], G["hd_t"][0]
+    ik = [np.array([250.0, 500.0, 750.0])] * 2
+    B = basis.tensor_bspline(t, [2, 2], np.array([[0.0, 990.0], [0.0, 990.0]]), ik)
+    Pm = basis.get_P([2, 2], ik)
+    n, T, K, P, M = 20, 144, 2, 36, 2
+    assert B.shape == (T, P)
+    eng = bf.Engine(model=FUNCTIONAL, n=n, K=K, P=P, M=M, y=y, B=B, T=T)
+    rng = np.random.default_rng(2)
+    Zref = S["HDFunctional_Z_med"]; Zref = Zref / Zref.sum(axis=1, keepdims=True)
+    eng.set_state(Zref, rng.normal(size=(n, M)))
+    smp = bf.Sampler(eng, hyper=bf.default_hyper(True), n_total=n, Pmat=Pm, seed=6)
+    smp.set(nu=S["HDFunctional_nu_med"], Phi=0.1 * rng.normal(size=(K, P, M)), sigma_sq=1.0,
+            pi=S["HDFunctional_pi_med"], alpha3=1.0)
+    sig = []
+    for _ in range(3000):
+        smp.step(bf.SWEEP_FULL)
+        sig.append(smp.get()["sigma_sq"])
+    med = np.median(sig[1500:])
+    lo, mid, hi = S["HDFunctional_sigma_q"]
+    assert lo * 0.85 < med < hi * 1.15, (med, lo, hi)
+    smp.close(); eng.close()
+
+
+def test_multivariate_matches_reference_stored_chain():
+    """BMVMMM example (MVSim_data.RDS: 20 x 10, K=2, M=2): sigma^2 posterior vs the stored chain
+    inst/test-data/Multivariate_trace/Sigma0.txt (second-half median 0.0242)."""
+    G = np.load(os.path.join(GOLD, "sim_inputs.npz")); S = np.load(os.path.join(GOLD, "trace_summaries.npz"))
+    y = G["mv_y"]
+    n, R, K, M = 20, 10, 2, 2
+    eng = bf.Engine(model=MULTIVARIATE, n=n, K=K, P=R, M=M, y=y)
+    rng = np.random.default_rng(3)
+    Zref = S["Multivariate_Z_med"]; Zref = Zref / Zref.sum(axis=1, keepdims=True)
+    eng.set_state(Zref, rng.normal(size=(n, M)))
+    smp = bf.Sampler(eng, hyper=bf.default_hyper(True), n_total=n, seed=8)
+    smp.set(nu=S["Multivariate_nu_med"], Phi=0.1 * rng.normal(size=(K, R, M)), sigma_sq=1.0,
+            pi=S["Multivariate_pi_med"], alpha3=1.0)
+    sig = []
+    for _ in range(4000):
+        smp.step(bf.SWEEP_FULL)
+        sig.append(smp.get()["sigma_sq"])
+    med = np.median(sig[2000:])
+    lo, mid, hi = S["Multivariate_sigma_q"]
+    assert lo * 0.6 < med < hi * 1.6, (med, lo, hi)     # n*R = 200 observations: a wide posterior
+    smp.close(); eng.close()
