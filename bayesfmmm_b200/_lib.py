@@ -23,10 +23,10 @@ class Config(C.Structure):
 # every symbol include/bfmmm.h and include/bfmmm_debug.h declare
 EXPORTS = [
     "bfmmm_create", "bfmmm_destroy", "bfmmm_last_error", "bfmmm_launch_count", "bfmmm_get_basis",
-    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
+    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_get_state_rows", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
     "bfmmm_ssr", "bfmmm_suffstats", "bfmmm_get_gram", "bfmmm_seed", "bfmmm_stats_buffer_dev",
     "bfmmm_update_z_async", "bfmmm_update_chi_async", "bfmmm_ssr_async", "bfmmm_suffstats_async",
-    "bfmmm_read_stats", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts", "bfmmm_suffstats_ragged",
+    "bfmmm_read_stats", "bfmmm_clear_ssr_after", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts", "bfmmm_suffstats_ragged",
     # include/bfmmm_sampler.h
     "bfmmm_hyper_defaults", "bfmmm_sampler_create", "bfmmm_sampler_create_detached", "bfmmm_sampler_destroy", "bfmmm_sampler_set_allreduce", "bfmmm_sampler_set_hband", "bfmmm_sampler_set_counts",
     "bfmmm_sampler_set", "bfmmm_sampler_get", "bfmmm_sampler_set_cov", "bfmmm_sampler_get_cov",

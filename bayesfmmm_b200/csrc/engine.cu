@@ -383,6 +383,18 @@ int bfmmm_get_state(bfmmm_engine* e, double* Z, double* chi) {
   return 0;
 }
 
+// rows [i0, i0 + count) of Z (count x K) and chi (count x M), column-major with leading dimension count:
+// a cheap read-back of a few functions (chain monitoring / ESS) instead of the whole state
+int bfmmm_get_state_rows(bfmmm_engine* e, int64_t i0, int64_t count, double* Z, double* chi) {
+  if (!e) return fail("null engine");
+  if (i0 < 0 || count < 0 || i0 + count > e->n) return fail("bfmmm_get_state_rows: range outside the shard");
+  CU(cudaSetDevice(e->device));
+  if (Z) CU(cudaMemcpy2DAsync(Z, (size_t)count * 8, e->Z + i0, (size_t)e->ld * 8, (size_t)count * 8, e->K, cudaMemcpyDeviceToHost, e->stream));
+  if (chi) CU(cudaMemcpy2DAsync(chi, (size_t)count * 8, e->chi + i0, (size_t)e->ld * 8, (size_t)count * 8, e->M, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 // whitened coefficient of feature f: c~ = L' c
 int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, const double* eta,
                       const double* xi, double sigma_sq) {
@@ -590,6 +602,15 @@ int bfmmm_suffstats_ragged(bfmmm_engine* e, double* WtW, double* BtYW, double* H
   if (WtW) std::copy(e->h_stats + e->off_wtw(), e->h_stats + e->off_ctw(), WtW);
   if (BtYW) std::copy(e->h_stats + e->off_ctw(), e->h_stats + e->off_hb(), BtYW);
   if (Hband) std::copy(e->h_stats + e->off_hb(), e->h_stats + e->stats_len, Hband);
+  return 0;
+}
+
+// zeroes the post-chi SSR slot of the statistics buffer (after it has been summed over the shards and
+// read, so that a later whole-buffer exchange does not add the global value once more)
+int bfmmm_clear_ssr_after(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemsetAsync(e->stats + e->off_ssr_after(), 0, 8, e->stream));
   return 0;
 }
 

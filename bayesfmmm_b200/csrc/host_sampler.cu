@@ -272,6 +272,10 @@ struct bfmmm_sampler {
   vecd stats;     // host copy of the engine statistics buffer
   vecd tt_ssr, tt_sigma;   // per-slot trace of the last tempered transition
   double last_ssr = 0;     // SSR of the state the last sweep ended with
+  // The SSR after the chi step only feeds the reported log-likelihood, never the chain: its read-back
+  // (and, on several GPUs, its all-reduce) is folded into the NEXT sweep's first exchange.
+  bool ll_pending = false;
+  double ll_sigma = 1.0;
   int64_t tt_accepts = 0, tt_total = 0;
   // wall-clock split of the sweeps run so far (seconds): host draws | waiting for the device (launch,
   // all-reduce, read-back) | pushing globals
@@ -431,15 +435,45 @@ int push_globals(bfmmm_sampler* s) {
                            s->D ? s->xi.data() : nullptr, s->sigma_sq);
 }
 
-int reduce_and_read(bfmmm_sampler* s) {
+// Sums the statistics over the shards (hook) and reads them back.  only_ssr: exchange just the SSR slot
+// (8 bytes).  Every slot must be summed exactly once after the kernel that wrote it: the full exchange
+// follows the Z / statistics kernels (and carries the previous sweep's post-chi SSR), the one-slot
+// exchange follows the SSR kernel.
+int reduce_and_read(bfmmm_sampler* s, bool only_ssr = false) {
   struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
   double* dev = nullptr; int64_t len = 0;
   if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
   if (s->allreduce) {
-    if (s->allreduce(s->allreduce_ctx, dev, len, bfmmm_stream(s->e))) return sfail("all-reduce hook failed");
+    int rc = only_ssr ? s->allreduce(s->allreduce_ctx, dev + s->K + 1, 1, bfmmm_stream(s->e))
+                      : s->allreduce(s->allreduce_ctx, dev, len, bfmmm_stream(s->e));
+    if (rc) return sfail("all-reduce hook failed");
   }
   s->stats.resize(len);
-  return bfmmm_read_stats(s->e, s->stats.data(), len);
+  return bfmmm_read_stats(s->e, s->stats.data(), only_ssr ? (int64_t)(s->K + 3) : len);
+}
+void set_loglik(bfmmm_sampler* s, double ssr_ll, double sigma_sq) {
+  // calcLikelihood (CalculateLikelihood.h:19-44; MV :137-159 with floor(P/2))
+  if (s->identity)
+    s->loglik = -((double)s->n_total * (double)(s->P / 2)) * std::log(2 * 3.14159265358979323846 * sigma_sq) -
+                ssr_ll / (2 * sigma_sq);
+  else
+    s->loglik = -s->n_points_total * (0.918938533204672741780329736406 + 0.5 * std::log(sigma_sq)) -
+                ssr_ll / (2 * sigma_sq);
+}
+// completes a deferred log-likelihood outside a sweep (bfmmm_sampler_get, tempered transitions)
+int flush_loglik(bfmmm_sampler* s) {
+  if (!s->ll_pending || !s->e) return 0;
+  struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
+  double* dev = nullptr; int64_t len = 0;
+  if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
+  if (s->allreduce && s->allreduce(s->allreduce_ctx, dev + s->K + 2, 1, bfmmm_stream(s->e))) return sfail("all-reduce hook failed");
+  vecd tmp(s->K + 3);
+  if (bfmmm_read_stats(s->e, tmp.data(), s->K + 3)) return 1;
+  s->last_ssr = tmp[s->K + 2];
+  set_loglik(s, s->last_ssr, s->ll_sigma);
+  s->ll_pending = false;
+  // the slot now holds the global sum on every rank: zero it so the next full exchange does not add it again
+  return bfmmm_clear_ssr_after(s->e);
 }
 const double* st_slz(bfmmm_sampler* s) { return s->stats.data(); }
 double st_acc(bfmmm_sampler* s) { return s->stats[s->K]; }
@@ -555,6 +589,7 @@ int bfmmm_sampler_set(bfmmm_sampler* s, const double* nu, const double* Phi, con
 int bfmmm_sampler_get(bfmmm_sampler* s, double* nu, double* Phi, double* sigma_sq, double* pi,
                       double* alpha3, double* delta, double* gamma, double* A, double* tau, double* loglik) {
   if (!s) return sfail("null sampler");
+  if (loglik && flush_loglik(s)) return 1;
   CP_OUT(nu, s->nu); CP_OUT(Phi, s->Phi); CP_OUT(pi, s->pi); CP_OUT(delta, s->delta); CP_OUT(gamma, s->gamma);
   CP_OUT(A, s->A); CP_OUT(tau, s->tau);
   if (sigma_sq) *sigma_sq = s->sigma_sq;
@@ -998,6 +1033,11 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   // the sufficient statistics depend only on (Z, chi, X): one pass feeds Phi, nu, eta and xi
   if (bfmmm_suffstats_async(e)) return 1;
   if (reduce_and_read(s)) return 1;
+  if (s->ll_pending) {                                     // previous sweep's post-chi SSR arrived with this exchange
+    s->last_ssr = st_ssr_after(s);
+    set_loglik(s, s->last_ssr, s->ll_sigma);
+    s->ll_pending = false;
+  }
   if (s->ragged) s->Hb = st_hb(s);
   if (do_z) s->last_accept = (int64_t)std::llround(st_acc(s));
   // The Gaussian blocks that change the mean (Phi, nu) are drawn first so that the SSR pass can start;
@@ -1020,13 +1060,22 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
     if (bfmmm_host_update_gamma(s)) return 1;
   }
   if (bfmmm_host_update_tau(s)) return 1;                  // updateTau (all three loops call it)
-  if (reduce_and_read(s)) return 1;
+  if (reduce_and_read(s, /*only_ssr=*/true)) return 1;
   if (bfmmm_host_update_sigma(s, st_ssr(s), beta, tempered)) return 1;
   double ssr_ll = st_ssr(s);
+  bool defer = false;
   if (do_chi) {                                            // updateChi (+ the SSR calcLikelihood needs)
     if (push_globals(s)) return 1;
     if (bfmmm_update_chi_async(e, beta)) return 1;
-    if (!s->D) { if (reduce_and_read(s)) return 1; ssr_ll = st_ssr_after(s); }
+    if (!s->D) {
+      if (s->in_tt) {                                      // a tempered transition needs every slot's SSR now
+        s->ll_pending = true; s->ll_sigma = s->sigma_sq;
+        if (flush_loglik(s)) return 1;
+        ssr_ll = s->last_ssr;
+      } else {
+        defer = true;                                      // read with the next sweep's first exchange
+      }
+    }
   }
   if (s->D) {
     // covariate-adjusted loops (BFMMM.h:3976-4000): after chi come updateEta, updateTauEta and the
@@ -1044,17 +1093,15 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
     }
     if (push_globals(s)) return 1;
     if (bfmmm_ssr_async(e)) return 1;
-    if (reduce_and_read(s)) return 1;
+    if (reduce_and_read(s, /*only_ssr=*/true)) return 1;
     ssr_ll = st_ssr(s);
   }
-  // calcLikelihood (CalculateLikelihood.h:19-44; MV :137-159 with floor(P/2))
-  s->last_ssr = ssr_ll;
-  if (s->identity)
-    s->loglik = -((double)s->n_total * (double)(s->P / 2)) * std::log(2 * 3.14159265358979323846 * s->sigma_sq) -
-                ssr_ll / (2 * s->sigma_sq);
-  else
-    s->loglik = -s->n_points_total * (0.918938533204672741780329736406 + 0.5 * std::log(s->sigma_sq)) -
-                ssr_ll / (2 * s->sigma_sq);
+  if (defer) {
+    s->ll_pending = true; s->ll_sigma = s->sigma_sq;
+  } else {
+    s->last_ssr = ssr_ll;
+    set_loglik(s, ssr_ll, s->sigma_sq);
+  }
   s->tick++;
   if (!s->in_tt) {
     if (s->rec.on && record_iteration(s)) return 1;
@@ -1075,10 +1122,11 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
   const double geom = std::pow(beta_N_t, 1.0 / N_t);
   for (int i = 1; i < N_t; i++) ladder[i] = ladder[i - 1] * geom;      // as written at BFMMM.h:1453-1460
   const int m = 2 * N_t;
+  if (flush_loglik(s)) return 1;
   // slot 0: the current state.  Its SSR: one data pass with the current globals.
   if (push_globals(s)) return 1;
   if (bfmmm_ssr_async(s->e)) return 1;
-  if (reduce_and_read(s)) return 1;
+  if (reduce_and_read(s, /*only_ssr=*/true)) return 1;
   s->tt_ssr.assign(m + 1, 0.0); s->tt_sigma.assign(m + 1, 0.0);
   s->tt_ssr[0] = st_ssr(s); s->tt_sigma[0] = s->sigma_sq;
   bfmmm_sampler saved = *s;                       // host-side copy of every global

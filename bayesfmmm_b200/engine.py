@@ -114,6 +114,12 @@ class Engine:
         self._chk(self._lib.bfmmm_get_state(self._h, _p(Zo), _p(co)))
         return Zo, co
 
+    def get_state_rows(self, i0, count, Z: bool = True, chi: bool = True):
+        Zo = np.zeros((count, self.K), order="F") if Z else None
+        co = np.zeros((count, self.M), order="F") if chi else None
+        self._chk(self._lib.bfmmm_get_state_rows(self._h, C.c_int64(i0), C.c_int64(count), _p(Zo), _p(co)))
+        return Zo, co
+
     def get_state_into(self, Z=None, chi=None):
         """D2H copy into caller-owned column-major buffers (the reference's chain slices)."""
         self._chk(self._lib.bfmmm_get_state(self._h, _p(Z), _p(chi)))

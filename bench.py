@@ -220,9 +220,11 @@ def run_ours(a):
         ptr, ln = eng.stats_buffer()
         stats_t = torch.as_tensor(_Buf(ptr, ln), device=torch.device("cuda", local))
 
-        def allreduce(p, l, stream):
-            with torch.cuda.stream(ext):
-                dist.all_reduce(stats_t)
+        torch.cuda.set_stream(ext)          # NCCL work is ordered on the engine's stream
+
+        def allreduce(p, l, stream):        # (device pointer, doubles): the whole buffer or one slot of it
+            off = (p - ptr) // 8
+            dist.all_reduce(stats_t[off:off + l])
         smp.set_allreduce(allreduce)
 
     def barrier():
@@ -271,6 +273,26 @@ def run_ours(a):
     h2d = 3 * P * (K * (M + 1)) * 8                      # three pushes of the global coefficients per sweep
     d2h = n * (K + M) * 8 + 3 * stats_len * 8            # Z and chi into the chain + three statistics read-backs
 
+    # ---- ESS/sec of Z (BASELINE.json names it; the reference has no ESS code): batch-means effective
+    # sample size of each Z_ik chain for 256 monitored functions over a further `ess_steps` sweeps,
+    # median over (i, k), per second of sweep time
+    ess_steps, nmon = 400, 256
+    zc = np.zeros((ess_steps, nmon, K))
+    t_e0 = time.perf_counter()
+    for it in range(ess_steps):
+        smp.step(bf.SWEEP_FULL)
+        zc[it] = eng.get_state_rows(0, nmon, chi=False)[0]
+    torch.cuda.synchronize()
+    t_ess = time.perf_counter() - t_e0
+    nb = 20
+    bm = zc.reshape(nb, ess_steps // nb, nmon, K).mean(axis=1)
+    var_chain = zc.var(axis=0, ddof=1)
+    var_bm = bm.var(axis=0, ddof=1) * (ess_steps // nb)
+    ess = np.where(var_bm > 0, ess_steps * var_chain / np.maximum(var_bm, 1e-300), float(ess_steps))
+    ess_z = {"median_ess": float(np.median(ess)), "sweeps": ess_steps, "monitored_functions": nmon,
+             "ess_per_sec": float(np.median(ess) / t_ess), "method": "batch means (20 batches), median over (i,k)",
+             "mean_accept_rate": smp.last_accept / (n * world)}
+
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline
     def kernel_ms(fn, reps=20):
         fn(); torch.cuda.synchronize()
@@ -299,8 +321,15 @@ def run_ours(a):
     kinfo = {k: {"ms": v[0], "algorithmic_bytes": v[1], "gbs": v[1] / (v[0] * 1e-3) / 1e9,
                  "frac": v[1] / (v[0] * 1e-3) / 1e9 / peak} for k, v in kern.items()}
     dom = max(kinfo, key=lambda k: kinfo[k]["ms"])
+    traffic = None
+    try:   # dram bytes of the same kernel from the committed `ncu --set full` capture (profiles/), same n
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get("n_per_gpu") == n:
+            traffic = tr["kernels"].get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kinfo[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kinfo[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kinfo[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kinfo[dom]["algorithmic_bytes"], "kernels": kinfo,
                 "device_ms_per_step_sum_of_kernels": sum(v["ms"] for v in kinfo.values())}
 
@@ -314,6 +343,7 @@ def run_ours(a):
            "host_split_ms_per_step": {k.replace("_s", ""): (prof1[k] - prof0[k]) / a.steps * 1e3 for k in prof1},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "steps": e_steps, "ms_per_step": ms_e / e_steps},
+           "ess_z": ess_z,
            "roofline": roofline}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:

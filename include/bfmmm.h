@@ -73,6 +73,8 @@ int bfmmm_get_basis(bfmmm_engine* e, double* B_out);
 /* ---- per-observation state (replaces the Z / chi chain slices the updates read and write) --- */
 int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi);
 int bfmmm_get_state(bfmmm_engine* e, double* Z, double* chi);     /* either may be NULL */
+/* rows [i0, i0+count) only: Z count x K, chi count x M (column-major, leading dimension count) */
+int bfmmm_get_state_rows(bfmmm_engine* e, int64_t i0, int64_t count, double* Z, double* chi);
 
 /* device-side snapshot / restore of (Z, chi): a rejected tempered transition keeps the
  * pre-transition slice (BFMMM.h:1631-1651) */
@@ -134,6 +136,7 @@ int bfmmm_update_chi_async(bfmmm_engine* e, double beta);
 int bfmmm_ssr_async(bfmmm_engine* e);
 int bfmmm_suffstats_async(bfmmm_engine* e);
 int bfmmm_read_stats(bfmmm_engine* e, double* out, int64_t len);   /* synchronises */
+int bfmmm_clear_ssr_after(bfmmm_engine* e);   /* zero the ssr_after slot once its global sum has been consumed */
 int bfmmm_sync(bfmmm_engine* e);
 /* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
 void* bfmmm_stream(bfmmm_engine* e);

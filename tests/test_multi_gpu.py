@@ -48,8 +48,9 @@ def _worker(rank, world, port, q, n_sweeps):
     t = torch.as_tensor(_Buf(ptr, ln), device=torch.device("cuda", rank))
 
     def allreduce(p, l, stream):
+        off = (p - ptr) // 8
         with torch.cuda.stream(ext):
-            dist.all_reduce(t)
+            dist.all_reduce(t[off:off + l])
     smp.set_allreduce(allreduce)
     for _ in range(n_sweeps):
         smp.step(bf.SWEEP_FULL)
