@@ -30,9 +30,24 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <int MT, int NT>
-__global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Operands travel global -> shared with cp.async (LDGSTS, 16 bytes per thread, L1 bypassed) into a
+// ring of ST stages of THREAD-PRIVATE slots: nothing is held in registers while in flight, so two
+// blocks of 8 warps are resident per SM with ST-1 chunks per warp in flight (the first version kept
+// the ring in registers: 170 registers, 8 warps/SM, long-scoreboard 55 %).  A thread only ever reads
+// the slots it filled itself, so no block barrier is needed: cp.async.wait_group orders its own copies.
+template <int MT, int NT, int ST, bool HASX>
+__global__ void __launch_bounds__(ST_THREADS, 2) stats_kernel(const StatsArgs a) {
   constexpr int TILES = MT * NT + NT * NT;
+  constexpr int PER = HASX ? 3 : 2;            // slots per n-tile: Z, chi (, x)
+  constexpr int ITEMS = MT + PER * NT;
+  extern __shared__ double2 ring[];            // [ST][ITEMS][ST_THREADS]
   __shared__ double s_acc[TILES * 64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, c = lane & 3;
@@ -75,39 +90,49 @@ __global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
 
   const int n_chunks = a.ld >> 3;
   const int wstride = gridDim.x * ST_WARPS;
-  // operands of one 8-function chunk; two chunks are kept in flight ahead of the one being multiplied
-  struct Ops { double2 av[MT], z[NT], ch[NT], x[NT]; };
-  auto fetch = [&](Ops& o, int chunk) {
-    const bool ok = chunk < n_chunks;
-    const int i = (chunk << 3) + 2 * c;
+  auto slot = [&](int stage, int item) { return ring + ((size_t)(stage * ITEMS + item) * ST_THREADS + threadIdx.x); };
+  auto issue = [&](int stage, int chunk) {
+    if (chunk < n_chunks) {
+      const int i = (chunk << 3) + 2 * c;
 #pragma unroll
-    for (int mt = 0; mt < MT; mt++)
-      o.av[mt] = (ok && ap[mt]) ? __ldcs(reinterpret_cast<const double2*>(ap[mt] + i)) : make_double2(0.0, 0.0);
+      for (int mt = 0; mt < MT; mt++)
+        if (ap[mt]) cp_async16(slot(stage, mt), ap[mt] + i);
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-      o.z[nt] = (ok && zp[nt]) ? ld2(zp[nt] + i) : make_double2(0.0, 0.0);
-      o.ch[nt] = (ok && cp[nt]) ? ld2(cp[nt] + i) : make_double2(1.0, 1.0);
-      o.x[nt] = (ok && xp[nt]) ? ld2(xp[nt] + i) : make_double2(1.0, 1.0);
+      for (int nt = 0; nt < NT; nt++) {
+        if (zp[nt]) cp_async16(slot(stage, MT + PER * nt), zp[nt] + i);
+        if (cp[nt]) cp_async16(slot(stage, MT + PER * nt + 1), cp[nt] + i);
+        if (HASX && xp[nt]) cp_async16(slot(stage, MT + PER * nt + 2), xp[nt] + i);
+      }
     }
+    cp_async_commit();          // one group per call (possibly empty) keeps the group count uniform
   };
-  Ops o0, o1, o2;
   int ch = blockIdx.x * ST_WARPS + warp;
-  fetch(o0, ch);
-  fetch(o1, ch + wstride);
+#pragma unroll
+  for (int st = 0; st < ST - 1; st++) issue(st, ch + st * wstride);
+  int stage = 0;
   for (; ch < n_chunks; ch += wstride) {
-    fetch(o2, ch + 2 * wstride);
-    double2 wv[NT];
+    int nxt = stage + (ST - 1); if (nxt >= ST) nxt -= ST;
+    issue(nxt, ch + (ST - 1) * wstride);
+    cp_async_wait<ST - 1>();    // the group of the current chunk has landed
+    double2 av[MT], wv[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) av[mt] = ap[mt] ? *slot(stage, mt) : make_double2(0.0, 0.0);
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
-      wv[nt].x = o0.z[nt].x * o0.ch[nt].x * o0.x[nt].x;
-      wv[nt].y = o0.z[nt].y * o0.ch[nt].y * o0.x[nt].y;
+      double2 w = make_double2(0.0, 0.0);
+      if (zp[nt]) {
+        w = *slot(stage, MT + PER * nt);
+        if (cp[nt]) { const double2 t = *slot(stage, MT + PER * nt + 1); w.x *= t.x; w.y *= t.y; }
+        if (HASX && xp[nt]) { const double2 t = *slot(stage, MT + PER * nt + 2); w.x *= t.x; w.y *= t.y; }
+      }
+      wv[nt] = w;
     }
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
-        dmma884(R[mt][nt][0], R[mt][nt][1], o0.av[mt].x, wv[nt].x);
-        dmma884(R[mt][nt][0], R[mt][nt][1], o0.av[mt].y, wv[nt].y);
+        dmma884(R[mt][nt][0], R[mt][nt][1], av[mt].x, wv[nt].x);
+        dmma884(R[mt][nt][0], R[mt][nt][1], av[mt].y, wv[nt].y);
       }
     if (do_wtw) {
 #pragma unroll
@@ -118,8 +143,9 @@ __global__ void __launch_bounds__(ST_THREADS) stats_kernel(const StatsArgs a) {
           dmma884(S[n1][n2][0], S[n1][n2][1], wv[n1].y, wv[n2].y);
         }
     }
-    o0 = o1; o1 = o2;
+    stage = stage + 1 == ST ? 0 : stage + 1;
   }
+  cp_async_wait<0>();
 
   // block reduction: warps add their fragments into shared memory one after the other (fixed order)
   for (int w = 0; w < ST_WARPS; w++) {
@@ -177,7 +203,7 @@ __global__ void __launch_bounds__(256) stats_final_kernel(const StatsArgs a, int
   if (lane == 0) { if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t; }
 }
 
-int stats_blocks(int sm_count) { return sm_count; }
+int stats_blocks(int sm_count) { return 2 * sm_count; }
 
 static inline void stats_shape(int P, int q, int& MT, int& NT, int& gy) {
   NT = (q + 7) / 8;
@@ -193,10 +219,28 @@ size_t stats_partial_doubles(int P, int q, int blocks) {
   return (size_t)gy * blocks * (MT * NT + NT * NT) * 64;
 }
 
+template <int MT, int NT, bool HASX>
+static int launch_stats_x(const StatsArgs& a, int gy, cudaStream_t s) {
+  dim3 grid(a.blocks, gy);
+  // three ring stages when two blocks of them fit in one SM's shared memory, otherwise two
+  constexpr size_t stage_bytes = (size_t)(MT + (HASX ? 3 : 2) * NT) * ST_THREADS * sizeof(double2);
+  constexpr bool three = 3 * stage_bytes <= 104 * 1024;
+  constexpr int ST = three ? 3 : 2;
+  const size_t smem = ST * stage_bytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stats_kernel<MT, NT, ST, HASX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  stats_kernel<MT, NT, ST, HASX><<<grid, ST_THREADS, smem, s>>>(a);
+  return 0;
+}
+
 template <int MT, int NT>
 static int launch_stats_t(const StatsArgs& a, int gy, cudaStream_t s) {
-  dim3 grid(a.blocks, gy);
-  stats_kernel<MT, NT><<<grid, ST_THREADS, 0, s>>>(a);
+  int rc = a.D > 0 ? launch_stats_x<MT, NT, true>(a, gy, s) : launch_stats_x<MT, NT, false>(a, gy, s);
+  if (rc) return rc;
   int tot = a.P * a.q + a.q * a.q;
   stats_final_kernel<MT, NT><<<(tot + 7) / 8, 256, 0, s>>>(a, a.blocks);
   g_launch_count += 2;
