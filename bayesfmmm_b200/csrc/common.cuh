@@ -57,7 +57,9 @@ struct Philox {
     lo = (uint32_t)p;
   }
   __host__ __device__ static inline void block(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int r = 0; r < 10; r++) {
       uint32_t hi0, lo0, hi1, lo1;
       mulhilo(0xD2511F53u, c[0], hi0, lo0);

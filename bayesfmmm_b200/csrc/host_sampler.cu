@@ -31,7 +31,6 @@ struct HostRng {
   bool use_tape = false;
   bf::RngStream stream{0, 0, 0, 0};
   void open(uint32_t purpose) { stream = bf::RngStream(key, 0xB200ull, iteration, purpose); }
-  bool taped() { return use_tape; }
   double pop() {
     if (tape.empty()) return std::numeric_limits<double>::quiet_NaN();
     double v = tape.front(); tape.pop_front(); return v;
@@ -43,49 +42,6 @@ struct HostRng {
 
 // ------------------------------------------------------------------ small dense linear algebra (column-major)
 using vecd = std::vector<double>;
-
-bool chol_lower(int n, const double* A, double* L) {
-  std::fill(L, L + (size_t)n * n, 0.0);
-  for (int j = 0; j < n; j++) {
-    double s = A[(size_t)j * n + j];
-    for (int k = 0; k < j; k++) s -= L[(size_t)k * n + j] * L[(size_t)k * n + j];
-    if (!(s > 0)) return false;
-    double d = std::sqrt(s);
-    L[(size_t)j * n + j] = d;
-    for (int i = j + 1; i < n; i++) {
-      double t = A[(size_t)j * n + i];
-      for (int k = 0; k < j; k++) t -= L[(size_t)k * n + i] * L[(size_t)k * n + j];
-      L[(size_t)j * n + i] = t / d;
-    }
-  }
-  return true;
-}
-
-// inverse of a symmetric positive definite matrix through its Cholesky factor: A = R R',
-// A^{-1} = R^{-T} R^{-1} (symmetric by construction)
-bool inv_spd(int n, const double* A, double* Ainv, vecd& work) {
-  work.resize((size_t)2 * n * n);
-  double* R = work.data();
-  double* Ri = work.data() + (size_t)n * n;
-  if (!chol_lower(n, A, R)) return false;
-  std::fill(Ri, Ri + (size_t)n * n, 0.0);
-  for (int c = 0; c < n; c++) {                 // Ri = R^{-1} (lower), column by column
-    Ri[(size_t)c * n + c] = 1.0 / R[(size_t)c * n + c];
-    for (int i = c + 1; i < n; i++) {
-      double s = 0;
-      for (int k = c; k < i; k++) s += R[(size_t)k * n + i] * Ri[(size_t)c * n + k];
-      Ri[(size_t)c * n + i] = -s / R[(size_t)i * n + i];
-    }
-  }
-  for (int c = 0; c < n; c++)
-    for (int r = c; r < n; r++) {
-      double s = 0;
-      for (int k = r; k < n; k++) s += Ri[(size_t)r * n + k] * Ri[(size_t)c * n + k];
-      Ainv[(size_t)c * n + r] = s;
-      Ainv[(size_t)r * n + c] = s;
-    }
-  return true;
-}
 
 // pseudo-inverse of a symmetric matrix (cyclic Jacobi); used when the precision is singular
 void pinv_sym_jacobi(int n, const double* A, double* Ainv) {
@@ -141,30 +97,6 @@ bool chol_rows(int n, const double* A, double* L) {
   }
   return true;
 }
-// C = (L L')^{-1} from the row-major factor: columns of L^{-1} by forward substitution (stored
-// column-major in W, column j occupies W[j*n + j .. j*n + n-1]), then C[i][j] = sum_{k >= max(i,j)} W_ki W_kj
-void inv_from_chol_rows(int n, const double* L, double* C, double* W) {
-  for (int j = 0; j < n; j++) {
-    double* x = W + (size_t)j * n;
-    for (int i = 0; i < j; i++) x[i] = 0.0;
-    for (int i = j; i < n; i++) {
-      const double* li = L + (size_t)i * n;
-      double s = (i == j) ? 1.0 : 0.0;
-      for (int k = j; k < i; k++) s -= li[k] * x[k];
-      x[i] = s / li[i];
-    }
-  }
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j <= i; j++) {
-      const double* xi = W + (size_t)i * n;
-      const double* xj = W + (size_t)j * n;
-      double s = 0;
-      for (int k = i; k < n; k++) s += xi[k] * xj[k];
-      C[(size_t)j * n + i] = s;
-      C[(size_t)i * n + j] = s;
-    }
-}
-
 // "Reverse" Cholesky A = U U' with U UPPER triangular, row-major (row i = U[i*n + i .. i*n + n-1]).
 // Why: the reference draws  x = C b + chol_lower(C) z  with C = A^{-1} (UpdateNu.h:67-69, UpdatePhi.h:79-82).
 // With A = U U',  C = U^{-T} U^{-1} = (U^{-T})(U^{-T})' and U^{-T} is lower triangular with positive
