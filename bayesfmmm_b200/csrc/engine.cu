@@ -31,6 +31,7 @@ constexpr int N_STAGE = 4;
 
 struct bfmmm_engine {
   int model = 0, n = 0, ld = 0, K = 0, P = 0, M = 0, D = 0, q = 0, QS = 0, device = 0;
+  int Pc = 0;   // rows of the projected cache = rank of the basis Gram (= P unless the basis is rank deficient)
   int64_t T = 0;
   bool common = true, identity = false;
   int64_t global_offset = 0;
@@ -48,7 +49,8 @@ struct bfmmm_engine {
   int64_t stats_len = 0;
   int pass_blocks = 0, st_blocks = 0;
   // host
-  std::vector<double> B, G, L;       // basis T x P row-major, Gram P x P col-major, chol lower col-major
+  std::vector<double> B, G, L;       // basis T x P row-major, Gram P x P col-major, whitening matrix P x Pc col-major
+                                     // (L = chol_lower(G), or V_r Lambda_r^{1/2} for a rank-deficient Gram): G = L L'
   double* h_stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
   int stage_next = 0;
@@ -143,28 +145,78 @@ int build_basis(bfmmm_engine* e, const bfmmm_config* c) {
       for (int r = 0; r < P; r++) e->G[(size_t)cc * P + r] += b[cc] * b[r];
     }
   }
-  if (!chol_lower(P, e->G, e->L))
-    return fail("bfmmm_create: B'B is not positive definite (a basis function has no support on the grid)");
+  e->Pc = P;
+  if (!chol_lower(P, e->G, e->L)) {
+    // rank-deficient Gram (a basis function without support on the grid, or T < P): G = V Lambda V',
+    // whitening matrix L := V_r Lambda_r^{1/2} (P x r) still satisfies G = L L' and B theta = Q (L' theta)
+    // with Q = B V_r Lambda_r^{-1/2}, so every identity the kernels rely on holds with r cache rows.
+    std::vector<double> a(e->G), V((size_t)P * P, 0.0);
+    for (int i = 0; i < P; i++) V[(size_t)i * P + i] = 1.0;
+    for (int sweep = 0; sweep < 100; sweep++) {
+      double off = 0;
+      for (int p = 0; p < P; p++) for (int q2 = p + 1; q2 < P; q2++) off += a[(size_t)q2 * P + p] * a[(size_t)q2 * P + p];
+      if (off < 1e-300) break;
+      for (int p = 0; p < P; p++)
+        for (int q2 = p + 1; q2 < P; q2++) {
+          double apq = a[(size_t)q2 * P + p];
+          if (apq == 0.0) continue;
+          double theta = (a[(size_t)q2 * P + q2] - a[(size_t)p * P + p]) / (2 * apq);
+          double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+          double cs = 1 / std::sqrt(t * t + 1), sn = t * cs;
+          for (int k = 0; k < P; k++) { double x = a[(size_t)p * P + k], y = a[(size_t)q2 * P + k]; a[(size_t)p * P + k] = cs * x - sn * y; a[(size_t)q2 * P + k] = sn * x + cs * y; }
+          for (int k = 0; k < P; k++) { double x = a[(size_t)k * P + p], y = a[(size_t)k * P + q2]; a[(size_t)k * P + p] = cs * x - sn * y; a[(size_t)k * P + q2] = sn * x + cs * y; }
+          for (int k = 0; k < P; k++) { double x = V[(size_t)p * P + k], y = V[(size_t)q2 * P + k]; V[(size_t)p * P + k] = cs * x - sn * y; V[(size_t)q2 * P + k] = sn * x + cs * y; }
+        }
+    }
+    double lmax = 0;
+    for (int i = 0; i < P; i++) lmax = std::max(lmax, a[(size_t)i * P + i]);
+    if (!(lmax > 0)) return fail("bfmmm_create: the basis is identically zero on the grid");
+    e->L.assign((size_t)P * P, 0.0);
+    int r = 0;
+    for (int j = 0; j < P; j++) {
+      double lam = a[(size_t)j * P + j];
+      if (lam <= 1e-10 * lmax) continue;
+      for (int i = 0; i < P; i++) e->L[(size_t)r * P + i] = V[(size_t)j * P + i] * std::sqrt(lam);
+      r++;
+    }
+    e->Pc = r;
+    e->L.resize((size_t)P * r);
+  }
   return 0;
 }
 
 int project_common(bfmmm_engine* e, const bfmmm_config* c) {
   const int P = e->P;
   const int64_t T = e->T;
-  // Q = B L^{-T}: row t of Q solves L q = b_t
-  std::vector<double> Q((size_t)T * P);
-  for (int64_t t = 0; t < T; t++) {
-    const double* b = &e->B[(size_t)t * P];
-    double* qv = &Q[(size_t)t * P];
-    for (int i = 0; i < P; i++) {
-      double s = b[i];
-      for (int k = 0; k < i; k++) s -= e->L[(size_t)k * P + i] * qv[k];
-      qv[i] = s / e->L[(size_t)i * P + i];
+  // Q (T x Pc) with orthonormal columns and B = Q L': full rank: row t of Q solves L q = b_t;
+  // rank-deficient: Q = B L (L'L)^{-1} with L'L = Lambda_r diagonal
+  const int Pc = e->Pc;
+  std::vector<double> Q((size_t)T * Pc);
+  if (Pc == P) {
+    for (int64_t t = 0; t < T; t++) {
+      const double* b = &e->B[(size_t)t * P];
+      double* qv = &Q[(size_t)t * P];
+      for (int i = 0; i < P; i++) {
+        double s = b[i];
+        for (int k = 0; k < i; k++) s -= e->L[(size_t)k * P + i] * qv[k];
+        qv[i] = s / e->L[(size_t)i * P + i];
+      }
+    }
+  } else {
+    std::vector<double> lam(Pc, 0.0);
+    for (int j = 0; j < Pc; j++) for (int i = 0; i < P; i++) lam[j] += e->L[(size_t)j * P + i] * e->L[(size_t)j * P + i];
+    for (int64_t t = 0; t < T; t++) {
+      const double* b = &e->B[(size_t)t * P];
+      for (int j = 0; j < Pc; j++) {
+        double s = 0;
+        for (int i = 0; i < P; i++) s += b[i] * e->L[(size_t)j * P + i];
+        Q[(size_t)t * Pc + j] = s / lam[j];
+      }
     }
   }
   double* d_Q = nullptr;
-  CU(cudaMalloc(&d_Q, (size_t)T * P * 8));
-  CU(cudaMemcpyAsync(d_Q, Q.data(), (size_t)T * P * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMalloc(&d_Q, (size_t)T * Pc * 8));
+  CU(cudaMemcpyAsync(d_Q, Q.data(), (size_t)T * Pc * 8, cudaMemcpyHostToDevice, e->stream));
   // stream the observations through a bounded device buffer
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(e->n, (int64_t)(1ull << 30) / (T * 8)));
   double* d_Y = nullptr;
@@ -173,7 +225,7 @@ int project_common(bfmmm_engine* e, const bfmmm_config* c) {
     int64_t m = std::min<int64_t>(chunk, e->n - i0);
     CU(cudaMemcpyAsync(d_Y, c->y + i0 * T, (size_t)m * T * 8, cudaMemcpyHostToDevice, e->stream));
     bf::ProjectArgs pa;
-    pa.n = (int)m; pa.ld = e->ld; pa.P = P; pa.T = T; pa.i_begin = i0; pa.Y = d_Y; pa.Q = d_Q; pa.Ct = e->Ct; pa.rss = e->rss;
+    pa.n = (int)m; pa.ld = e->ld; pa.P = Pc; pa.T = T; pa.i_begin = i0; pa.Y = d_Y; pa.Q = d_Q; pa.Ct = e->Ct; pa.rss = e->rss;
     if (bf::launch_project(pa, e->stream)) return fail("project kernel launch failed");
     CU(cudaStreamSynchronize(e->stream));
   }
@@ -318,6 +370,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     e->G.assign((size_t)e->P * e->P, 0.0);
     e->L.assign((size_t)e->P * e->P, 0.0);
     for (int p = 0; p < e->P; p++) { e->G[(size_t)p * e->P + p] = 1; e->L[(size_t)p * e->P + p] = 1; }
+    e->Pc = e->P;
     if (upload_cols(e, e->Ct, c->y, e->P)) return bail(1);      // c~_i = y_i, rss_i = 0
     e->n_points = (double)e->n * e->P;
     e->sum_half = (double)(((int64_t)e->n * e->P) / 2);          // y_obs.n_elem / 2, UpdateSigma.h:150
@@ -325,6 +378,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     e->G.assign((size_t)e->P * e->P, 0.0);
     e->L.assign((size_t)e->P * e->P, 0.0);
     for (int p = 0; p < e->P; p++) e->L[(size_t)p * e->P + p] = 1;      // no common whitening
+    e->Pc = e->P;
     if (project_ragged(e, c)) return bail(1);
     e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q + (int64_t)e->npairs * e->bw * e->P;
   } else {
@@ -421,16 +475,16 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
     if (e->identity || e->ragged) {
       for (int p = 0; p < P; p++) h[(size_t)p * QS + f] = cvec[p];
     } else {
-      for (int p = 0; p < P; p++) {
+      for (int p = 0; p < e->Pc; p++) {           // (L' c)[p] = sum_r L[r][p] c[r]
         double s = 0;
-        for (int r = p; r < P; r++) s += e->L[(size_t)p * P + r] * cvec[r];   // (L')[p][r] = L[r][p]
+        for (int r = (e->Pc == P ? p : 0); r < P; r++) s += e->L[(size_t)p * P + r] * cvec[r];
         h[(size_t)p * QS + f] = s;
       }
     }
   }
-  for (int p = 0; p < P; p++)
+  for (int p = 0; p < e->Pc; p++)
     for (int f = e->q; f < QS; f++) h[(size_t)p * QS + f] = 0.0;
-  CU(cudaMemcpyAsync(e->glob, h, (size_t)P * QS * 8, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->glob, h, (size_t)e->Pc * QS * 8, cudaMemcpyHostToDevice, e->stream));
   CU(cudaEventRecord(e->ev_stage[slot], e->stream));
   e->sigma_sq = sigma_sq;
   return 0;
@@ -438,7 +492,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
 
 static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
-  a.n = e->n; a.ld = e->ld; a.P = e->P; a.D = e->D; a.QS = e->QS;
+  a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.D = e->D; a.QS = e->QS;
   a.sm_count = e->sm_count; a.max_blocks = e->pass_blocks;
   a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
   a.sigma_sq = e->sigma_sq; a.beta = beta;
@@ -537,7 +591,7 @@ int bfmmm_suffstats_async(bfmmm_engine* e) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   bf::StatsArgs a;
-  a.n = e->n; a.ld = e->ld; a.P = e->P; a.K = e->K; a.M = e->M; a.D = e->D; a.q = e->q;
+  a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.K = e->K; a.M = e->M; a.D = e->D; a.q = e->q;
   a.Ct = e->ragged ? e->Hh : e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
   a.WtW = e->stats + e->off_wtw(); a.CtW = e->stats + e->off_ctw(); a.blocks = e->st_blocks;
   int rc = bf::launch_stats(a, e->stream);
@@ -552,14 +606,15 @@ int bfmmm_suffstats_async(bfmmm_engine* e) {
   return 0;
 }
 
-// B'Y'W = L * (C~'W)
+// B'Y'W = L * (C~'W): L is P x Pc (lower triangular when Pc == P), C~'W is Pc x q with leading dimension Pc
 static void unwhiten(const bfmmm_engine* e, const double* CtW, double* BtYW) {
-  const int P = e->P;
+  const int P = e->P, Pc = e->Pc;
   for (int f = 0; f < e->q; f++)
     for (int r = 0; r < P; r++) {
       if (e->identity || e->ragged) { BtYW[(size_t)f * P + r] = CtW[(size_t)f * P + r]; continue; }
       double s = 0;
-      for (int k = 0; k <= r; k++) s += e->L[(size_t)k * P + r] * CtW[(size_t)f * P + k];
+      const int kmax = (Pc == P) ? r + 1 : Pc;
+      for (int k = 0; k < kmax; k++) s += e->L[(size_t)k * P + r] * CtW[(size_t)f * Pc + k];
       BtYW[(size_t)f * P + r] = s;
     }
 }
@@ -693,7 +748,7 @@ int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out) {
 int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
-  if (Ct && download_cols(e, Ct, e->Ct, e->P)) return 1;
+  if (Ct && download_cols(e, Ct, e->Ct, e->Pc)) return 1;
   if (rss && download_cols(e, rss, e->rss, 1)) return 1;
   CU(cudaStreamSynchronize(e->stream));
   return 0;

@@ -82,8 +82,6 @@ def test_invalid_configurations_fail_loudly():
         bf.Engine(model=FUNCTIONAL, n=10, K=7, P=6, M=2, y=s["y"], B=s["B"], T=20)
     with pytest.raises(bf.EngineError):      # no basis and no spline description
         bf.Engine(model=FUNCTIONAL, n=10, K=3, P=6, M=2, y=s["y"], T=20)
-    with pytest.raises(bf.EngineError):      # rank-deficient basis (P > T)
-        bf.Engine(model=FUNCTIONAL, n=10, K=3, P=6, M=2, y=s["y"][:, :4], B=s["B"][:4], T=4)
     with pytest.raises(bf.EngineError):      # bad device
         bf.Engine(model=FUNCTIONAL, n=10, K=3, P=6, M=2, y=s["y"], B=s["B"], T=20, device=99)
     eng = bf.Engine(model=FUNCTIONAL, n=10, K=3, P=6, M=2, y=s["y"], B=s["B"], T=20)
@@ -172,3 +170,40 @@ def test_full_size_properties():
     ssr_after = full.update_chi(1.0)
     assert rel(ssr_after, full.ssr()[0]) < 1e-11
     full.close()
+
+
+@pytest.mark.parametrize("kind", ["no_support", "fewer_points_than_basis"])
+def test_rank_deficient_basis(kind):
+    """A basis whose Gram matrix is singular on the grid (a basis function without support, or T < P):
+    the reference works with B directly, the engine falls back to an eigen-whitening of rank r < P."""
+    rng = np.random.default_rng(7)
+    n, K, P, M = 40, 3, 8, 2
+    ik = synth.equispaced_internal(P, 3)
+    if kind == "no_support":
+        t = np.linspace(0.0, 450.0, 30)            # the last basis functions vanish on [0, 450]
+    else:
+        t = np.linspace(0.0, 1000.0, 5)            # T = 5 < P = 8
+    B = synth.bspline_design(t, ik, 3)
+    assert np.linalg.matrix_rank(B) < P
+    par = synth.make_params(rng, K, P, M, 0, 0.01)
+    pi, Z, chi = synth.make_state(rng, n, K, M)
+    y = synth.theta(par, Z, chi) @ B.T + 0.1 * rng.normal(size=(n, len(t)))
+    s = dict(n=n, K=K, P=P, M=M, T=len(t), B=B, y=y, X=None, par=par, Z=Z, chi=chi, pi=pi)
+    d, st = _oracle(s)
+    eng = _mk(s)
+    assert rel(eng.ssr()[0], orc.ssr(d, st)[0]) < TOL
+    eps = np.asfortranarray(rng.normal(size=(n, M)))
+    ssr_after = eng.update_chi(1.0, eps=eps)
+    chi_o = orc.update_chi(d, st, eps)
+    assert rel(eng.get_state(Z=False)[1], chi_o) < 1e-9
+    eng.set_state(Z, chi)
+    gam = np.asfortranarray(rng.gamma(20000.0 * Z)); u = rng.uniform(size=n)
+    Zo, acc, _ = orc.update_z(d, st, pi, 1.0, 20000.0, gam, u)
+    eng.update_z(pi, 1.0, 20000.0, 1.0, gam=gam, u=u)
+    ok = ~(np.abs(np.log(u) - acc) <= 1e-7)
+    assert np.array_equal(eng.get_state(chi=False)[0][ok], Zo[ok])
+    eng.set_state(Z, chi)
+    W, R = eng.suffstats()
+    Wm = np.concatenate([np.stack([Z[:, k]] + [Z[:, k] * chi[:, m] for m in range(M)], axis=1) for k in range(K)], axis=1)
+    assert rel(R, (y @ B).T @ Wm) < 1e-9 and rel(eng.gram(), B.T @ B) < 1e-12
+    eng.close()
