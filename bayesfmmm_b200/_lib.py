@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libbfmmm_b200.so")
+_LIB = os.environ.get("BFMMM_LIB") or os.path.join(_HERE, "libbfmmm_b200.so")   # BFMMM_LIB: tuning builds only
 _lib = None
 
 dp = C.POINTER(C.c_double)
