@@ -23,7 +23,7 @@ class Config(C.Structure):
 # every symbol include/bfmmm.h and include/bfmmm_debug.h declare
 EXPORTS = [
     "bfmmm_create", "bfmmm_destroy", "bfmmm_last_error", "bfmmm_launch_count", "bfmmm_get_basis",
-    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_get_state_rows", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
+    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_get_state_rows", "bfmmm_get_state_begin", "bfmmm_get_state_wait", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
     "bfmmm_ssr", "bfmmm_suffstats", "bfmmm_get_gram", "bfmmm_seed", "bfmmm_stats_buffer_dev",
     "bfmmm_update_z_async", "bfmmm_update_chi_async", "bfmmm_ssr_async", "bfmmm_suffstats_async",
     "bfmmm_read_stats", "bfmmm_clear_ssr_after", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts", "bfmmm_suffstats_ragged",
@@ -42,7 +42,7 @@ EXPORTS = [
     "bfmmm_host_update_gamma_xi", "bfmmm_host_update_A_xi", "bfmmm_host_update_phi", "bfmmm_host_update_nu",
     "bfmmm_host_update_eta", "bfmmm_host_update_xi", "bfmmm_host_update_sigma",
     "bfmmm_debug_enable_acc", "bfmmm_debug_get_acc", "bfmmm_debug_update_z_rng", "bfmmm_debug_update_chi_rng",
-    "bfmmm_debug_get_cache",
+    "bfmmm_debug_get_cache", "bfmmm_debug_fastmath",
 ]
 
 

@@ -2,7 +2,7 @@
 //
 // Data layout in HBM:
 //   Ct   [P][ld]  whitened projected coefficients  c~_i = L^{-1} B' y_i   (SoA: coefficient-major,
-//                 function index contiguous, ld = n rounded up to 8) -- the per-iteration kernels
+//                 function index contiguous, ld = n rounded up to 64) -- the per-iteration kernels
 //                 stream this cache instead of the raw observations.
 //   rss  [ld]     ||y_i - B c_i||^2, the part of the residual orthogonal to the basis
 //   Z    [K][ld], chi [M][ld], X [D][ld]   (the reference's column-major n x K etc. with padded ld)
@@ -27,12 +27,14 @@ struct PassArgs {
   int bw;                           // ragged grids: band width (degree + 1)
   const double* __restrict__ rss;
   double* __restrict__ Z;
+  double* __restrict__ lZ;          // log Z [K][ld], kept next to Z by every writer of Z (set_state, Z step, restore)
   double* __restrict__ chi;
   const double* __restrict__ X;
   const double* __restrict__ glob;
   double sigma_sq, beta;
   // Z step
   double alpha3, a_Z_PM, log_a_Z_PM;
+  double lgam_a, digam_a, trigam_a; // log Gamma, digamma, trigamma at a_Z_PM (host): lgamma(a sum_k z_k) by its Taylor series
   double pi[8];
   const double* __restrict__ gam;   // injected draws [K][ld] or nullptr (device RNG)
   const double* __restrict__ u;     // [ld] or nullptr
@@ -332,6 +334,8 @@ size_t ragged_stats_partial_doubles(int P, int bw, int q, int sm_count);
 int launch_band_width(const double* B, int64_t rows, int P, int* bw_dev, cudaStream_t s);
 int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots, int degree, int P,
                    double* B_rowmajor, cudaStream_t s);
+int launch_copy_to_host(const double* src, double* dst_mapped, int64_t len, cudaStream_t s);   // SM-driven D2H of a few KB
+int launch_log_rows(const double* src, double* dst, size_t count, cudaStream_t s);   // dst = log(src), elementwise
 
 extern unsigned long long g_launch_count;
 int set_error(const char* msg);   // records the message returned by bfmmm_last_error(); returns 1

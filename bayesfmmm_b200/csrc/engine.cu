@@ -39,11 +39,15 @@ struct bfmmm_engine {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   // device
-  double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
+  double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *lZ = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
   double *Hh = nullptr, *Gl = nullptr, *rs_partials = nullptr;   // ragged grids: B_i'y_i, band of G_i
   int bw = 0, npairs = 0;
   bool ragged = false;
-  double *snapZ = nullptr, *snapChi = nullptr;   // device copy of (Z, chi) for tempered transitions
+  double *snapZ = nullptr, *snapLZ = nullptr, *snapChi = nullptr;   // device copy of (Z, log Z, chi) for tempered transitions
+  double *rbZ = nullptr, *rbChi = nullptr;       // device staging of an overlapped read-back (bfmmm_get_state_begin)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+  bool rb_pending = false;
   double *draws = nullptr, *stats = nullptr, *partials = nullptr, *st_partials = nullptr, *acc_dbg = nullptr;
   unsigned int* ticket = nullptr;
   int64_t stats_len = 0;
@@ -55,6 +59,7 @@ struct bfmmm_engine {
   cudaEvent_t ev_stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr};
   int stage_next = 0;
   double* h_stats = nullptr;
+  double* h_stats_dev = nullptr;   // device alias of h_stats (mapped page-locked memory)
   double sigma_sq = 1.0;
   uint64_t key = 0x9E3779B97F4A7C15ull, iteration = 0;
   // offsets into stats
@@ -89,10 +94,14 @@ bool chol_lower(int n, const std::vector<double>& A, std::vector<double>& L) {
 void free_all(bfmmm_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
+  cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->lZ); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
   cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
-  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi);
+  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapLZ); cudaFree(e->snapChi);
   cudaFree(e->Hh); cudaFree(e->Gl); cudaFree(e->rs_partials);
+  if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+  if (e->ev_snap) cudaEventDestroy(e->ev_snap);
+  if (e->ev_copied) cudaEventDestroy(e->ev_copied);
+  cudaFree(e->rbZ); cudaFree(e->rbChi);
   for (int i = 0; i < N_STAGE; i++) {
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
@@ -321,7 +330,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   e->common = e->identity || c->common_grid;
   e->T = e->identity ? c->P : c->T;
   e->global_offset = c->global_offset;
-  e->ld = (c->n + 7) & ~7;
+  e->ld = (c->n + 63) & ~63;      // padded with zero functions: 8-function DMMA chunks, 64-function TMA stages
   e->q = c->K * (1 + c->D) * (1 + c->M);
   e->QS = (e->q + 1) & ~1;
   e->ragged = !e->common;
@@ -341,6 +350,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMalloc(&e->Ct, ld * e->P * 8));
   CUE(cudaMalloc(&e->rss, ld * 8));
   CUE(cudaMalloc(&e->Z, ld * e->K * 8));
+  CUE(cudaMalloc(&e->lZ, ld * e->K * 8));
   CUE(cudaMalloc(&e->chi, ld * e->M * 8));
   if (e->D) CUE(cudaMalloc(&e->X, ld * e->D * 8));
   CUE(cudaMalloc(&e->glob, (size_t)e->P * e->QS * 8));
@@ -357,6 +367,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMemsetAsync(e->Ct, 0, ld * e->P * 8, e->stream));
   CUE(cudaMemsetAsync(e->rss, 0, ld * 8, e->stream));
   CUE(cudaMemsetAsync(e->Z, 0, ld * e->K * 8, e->stream));
+  if (bf::launch_log_rows(e->Z, e->lZ, ld * e->K, e->stream)) { fail("log kernel launch failed"); return bail(1); }
   CUE(cudaMemsetAsync(e->chi, 0, ld * e->M * 8, e->stream));
   CUE(cudaMemsetAsync(e->stats, 0, e->stats_len * 8, e->stream));
   CUE(cudaMemsetAsync(e->draws, 0, ld * (std::max(e->K + 1, e->M)) * 8, e->stream));
@@ -365,7 +376,8 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     CUE(cudaMallocHost(&e->h_stage[i], (size_t)e->P * e->QS * 8));
     CUE(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
   }
-  CUE(cudaMallocHost(&e->h_stats, e->stats_len * 8));
+  CUE(cudaHostAlloc(&e->h_stats, e->stats_len * 8, cudaHostAllocMapped));
+  CUE(cudaHostGetDevicePointer(&e->h_stats_dev, e->h_stats, 0));
   if (e->identity) {
     e->G.assign((size_t)e->P * e->P, 0.0);
     e->L.assign((size_t)e->P * e->P, 0.0);
@@ -424,6 +436,7 @@ int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   if (Z && upload_cols(e, e->Z, Z, e->K)) return 1;
+  if (Z && bf::launch_log_rows(e->Z, e->lZ, (size_t)e->ld * e->K, e->stream)) return fail("log kernel launch failed");
   if (chi && upload_cols(e, e->chi, chi, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
   return 0;
@@ -434,6 +447,37 @@ int bfmmm_get_state(bfmmm_engine* e, double* Z, double* chi) {
   if (Z && download_cols(e, Z, e->Z, e->K)) return 1;
   if (chi && download_cols(e, chi, e->chi, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// Overlapped read-back: device-side snapshot on the compute stream, host transfer on a copy stream.
+int bfmmm_get_state_begin(bfmmm_engine* e, double* Z, double* chi) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (!e->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_snap, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming));
+    CU(cudaMalloc(&e->rbZ, (size_t)e->ld * e->K * 8));
+    CU(cudaMalloc(&e->rbChi, (size_t)e->ld * e->M * 8));
+  }
+  if (e->rb_pending) CU(cudaStreamWaitEvent(e->stream, e->ev_copied, 0));   // the staging buffers are being read
+  if (Z) CU(cudaMemcpyAsync(e->rbZ, e->Z, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
+  if (chi) CU(cudaMemcpyAsync(e->rbChi, e->chi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
+  CU(cudaEventRecord(e->ev_snap, e->stream));
+  CU(cudaStreamWaitEvent(e->copy_stream, e->ev_snap, 0));
+  if (Z) CU(cudaMemcpy2DAsync(Z, (size_t)e->n * 8, e->rbZ, (size_t)e->ld * 8, (size_t)e->n * 8, e->K, cudaMemcpyDeviceToHost, e->copy_stream));
+  if (chi) CU(cudaMemcpy2DAsync(chi, (size_t)e->n * 8, e->rbChi, (size_t)e->ld * 8, (size_t)e->n * 8, e->M, cudaMemcpyDeviceToHost, e->copy_stream));
+  CU(cudaEventRecord(e->ev_copied, e->copy_stream));
+  e->rb_pending = true;
+  return 0;
+}
+int bfmmm_get_state_wait(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  if (!e->rb_pending) return 0;
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventSynchronize(e->ev_copied));
+  e->rb_pending = false;
   return 0;
 }
 
@@ -494,10 +538,20 @@ static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
   a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.D = e->D; a.QS = e->QS;
   a.sm_count = e->sm_count; a.max_blocks = e->pass_blocks;
-  a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
+  a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.lZ = e->lZ; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
   a.sigma_sq = e->sigma_sq; a.beta = beta;
   a.key = e->key; a.iteration = e->iteration; a.global_offset = (uint64_t)e->global_offset;
   a.partials = e->partials; a.ticket = e->ticket;
+}
+
+// digamma and trigamma at x > 0: upward recurrence to x >= 12, then the asymptotic series
+static void polygamma01(double x, double& digam, double& trigam) {
+  double d = 0, t = 0;
+  while (x < 12.0) { d -= 1.0 / x; t += 1.0 / (x * x); x += 1.0; }
+  const double r = 1.0 / x, r2 = r * r;
+  d += std::log(x) - 0.5 * r - r2 * (1.0 / 12 - r2 * (1.0 / 120 - r2 * (1.0 / 252 - r2 * (1.0 / 240 - r2 * (1.0 / 132)))));
+  t += r + 0.5 * r2 + r2 * r * (1.0 / 6 - r2 * (1.0 / 30 - r2 * (1.0 / 42 - r2 * (1.0 / 30 - r2 * (5.0 / 66)))));
+  digam = d; trigam = t;
 }
 
 static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta, bool injected,
@@ -505,6 +559,7 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
   bf::PassArgs a;
   fill_pass(e, a, beta);
   a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM);
+  a.lgam_a = std::lgamma(a_Z_PM); polygamma01(a_Z_PM, a.digam_a, a.trigam_a);
   for (int k = 0; k < e->K; k++) a.pi[k] = pi[k];
 #ifdef BF_TUNE_V
   static const bool force_inject = std::getenv("BFMMM_Z_INJECT") != nullptr;   // tuning: time the step without the RNG
@@ -635,8 +690,10 @@ int bfmmm_state_snapshot(bfmmm_engine* e) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   if (!e->snapZ) CU(cudaMalloc(&e->snapZ, (size_t)e->ld * e->K * 8));
+  if (!e->snapLZ) CU(cudaMalloc(&e->snapLZ, (size_t)e->ld * e->K * 8));
   if (!e->snapChi) CU(cudaMalloc(&e->snapChi, (size_t)e->ld * e->M * 8));
   CU(cudaMemcpyAsync(e->snapZ, e->Z, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->snapLZ, e->lZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
   CU(cudaMemcpyAsync(e->snapChi, e->chi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
@@ -644,6 +701,7 @@ int bfmmm_state_restore(bfmmm_engine* e) {
   if (!e || !e->snapZ) return fail("bfmmm_state_restore: no snapshot");
   CU(cudaSetDevice(e->device));
   CU(cudaMemcpyAsync(e->Z, e->snapZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->lZ, e->snapLZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
   CU(cudaMemcpyAsync(e->chi, e->snapChi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
@@ -684,7 +742,8 @@ int bfmmm_read_stats(bfmmm_engine* e, double* out, int64_t len) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   if (len > e->stats_len) len = e->stats_len;
-  CU(cudaMemcpyAsync(e->h_stats, e->stats, len * 8, cudaMemcpyDeviceToHost, e->stream));
+  // SM-driven store into mapped host memory: does not queue behind an overlapped state transfer
+  if (bf::launch_copy_to_host(e->stats, e->h_stats_dev, len, e->stream)) return fail("copy_to_host kernel launch failed");
   CU(cudaStreamSynchronize(e->stream));
   // the C~'W block is returned un-whitened (B'Y'W), like bfmmm_suffstats
   std::vector<double> tmp;

@@ -8,6 +8,7 @@
 #include <utility>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace bf {
 
@@ -215,22 +216,96 @@ __device__ __forceinline__ void stage_globals(const PassArgs& a, double* g) {
 // Z_proposal_density :102-113; rdirichlet Distributions.h:22-45; calc_lB :51-61).
 // The squared-error terms are evaluated in the whitened coefficient space, where
 // ||y - B theta||^2 = rss_i + ||c~_i - theta~||^2 and rss_i cancels in the ratio.
+// log Z of the current state is read from the cache a.lZ (and written back with Z), every other
+// transcendental goes through fastmath.cuh.
+
+// Rows of the coefficient cache in groups of four, two groups alternating (A is consumed while B is in
+// flight and vice versa: no register copies).  begin() issues the first group, so the caller can put
+// independent work (the proposal) between it and run().  P % 4 == 0 takes a predicate-free path.
+template <int V>
+struct RowStream {
+  double A[4][V], B[4][V];
+  const double* q;
+  size_t s1;
+  template <bool FULL>
+  __device__ __forceinline__ void fetch(const double* r, int p, int P, double (&c)[4][V]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (FULL || p + j < P) ldv_cs<V>(r + j * s1, c[j]);
+  }
+  __device__ __forceinline__ void begin(const double* col, int ld, int P) {
+    q = col; s1 = (size_t)ld;
+    if ((P & 3) == 0) fetch<true>(q, 0, P, A); else fetch<false>(q, 0, P, A);
+  }
+  template <bool FULL, typename F>
+  __device__ __forceinline__ void loop(int P, F&& body) {
+    for (int p = 0; p < P; p += 8) {
+      if (p + 4 < P) fetch<FULL>(q + 4 * s1, p + 4, P, B);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (FULL || p + j < P) body(p + j, A[j]);
+      q += 8 * s1;
+      if (p + 8 < P) fetch<FULL>(q, p + 8, P, A);
+      if (p + 4 < P) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (FULL || p + 4 + j < P) body(p + 4 + j, B[j]);
+      }
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void run(int P, F&& body) {
+    if ((P & 3) == 0) loop<true>(P, body); else loop<false>(P, body);
+  }
+};
+
+// generic proposal sampler (rejected fast-path candidate, or K > 4): out of line, rarely executed
+template <int K>
+__device__ __noinline__ void z_slow_proposal(uint64_t key, uint64_t gi, uint64_t iteration, const double* sh, double* zp,
+                                             double* uacc, bool live) {
+  RngStream rs(key, gi, iteration, RNG_Z_PROPOSAL_SLOW);
+#pragma unroll
+  for (int k = 0; k < K; k++) zp[k] = live ? rs.gamma(sh[k]) : 1.0;
+  if (K > 4) *uacc = rs.uniform();
+}
+static __device__ __noinline__ double nl_pow_u(double u, double inv_shape) { return exp(log(u) * inv_shape); }
+
+// log Gamma(tot) for tot = a * sum_k z_k, which equals a up to rounding when the row of Z sums to one:
+// second-order Taylor series around a (error |dt|^3 / (6 a^2)), the general routine otherwise
+__device__ __forceinline__ double lgamma_near_a(double tot, const PassArgs& a) {
+  const double dt = tot - a.a_Z_PM;
+  if (fabs(dt) <= 1e-8 * a.a_Z_PM) return fma(dt, fma(0.5 * dt, a.trigam_a, a.digam_a), a.lgam_a);
+  return lgamma_pos(tot, fast_log(tot));
+}
+
+#ifndef BF_Z_MINB
+#define BF_Z_MINB 8       // resident blocks per SM the register allocation of the V = 1 common-grid Z kernel targets
+#endif
 template <int K, int M, bool COV, int V, bool RG>
-__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
+  build_log_table();
   stage_globals(a, g);
   double red[K + 1];
 #pragma unroll
   for (int j = 0; j <= K; j++) red[j] = 0;
+  const double hb = a.beta / (2 * a.sigma_sq);
   // persistent blocks: every thread walks the functions with a grid stride, one reduction per block
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);
+    RowStream<V> rows;
+    if constexpr (!RG) rows.begin(a.Ct + i0, a.ld, a.P);      // first rows in flight during the proposal
     double zp[V][K], uacc[V], lzo[V][K], lzn[V][K];
+    {
+      double t[V];
 #pragma unroll
-    for (int v = 0; v < V; v++)
+      for (int k = 0; k < K; k++) {
+        ldv<V>(a.lZ + (size_t)k * a.ld + i0, t);
 #pragma unroll
-      for (int k = 0; k < K; k++) lzo[v][k] = nl_log(st.z[v][k]);
+        for (int v = 0; v < V; v++) lzo[v][k] = t[v];
+      }
+    }
     // ---- proposal
     if (a.gam) {
       double t[V];
@@ -247,34 +322,34 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
 #pragma unroll
         for (int k = 0; k < K; k++) sum += zp[v][k];
 #pragma unroll
-        for (int k = 0; k < K; k++) { zp[v][k] = zp[v][k] / sum; lzn[v][k] = nl_log(zp[v][k]); }
+        for (int k = 0; k < K; k++) { zp[v][k] = zp[v][k] / sum; lzn[v][k] = fast_log(zp[v][k]); }
       }
     } else {
 #pragma unroll
       for (int v = 0; v < V; v++) {
         const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
-        double lg[K], sum = 0;
-        bool fast = (K <= 4) && (i0 + v < a.n);
+        const bool live = (i0 + v) < a.n;
+        bool fast = (K <= 4);
         bool small = false;
-        double sh[K], lsh[K];
+        double sh[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
-          sh[k] = a.a_Z_PM * st.z[v][k]; lsh[k] = a.log_a_Z_PM + lzo[v][k];
-          if (sh[k] <= 0) { sh[k] = 10; lsh[k] = 2.302585092994045684; }   // Distributions.h:24-28
+          sh[k] = a.a_Z_PM * st.z[v][k];
+          if (!(sh[k] > 0)) sh[k] = 10;                                   // Distributions.h:24-28
           small = small || (sh[k] < 1.0);
         }
         if constexpr (K <= 4) {
           // straight-line path: three Philox blocks give two Box-Muller pairs (4 normals), four 32-bit
-          // accept uniforms and the 53-bit Metropolis uniform; one Marsaglia-Tsang candidate per coordinate
+          // accept uniforms and the Metropolis uniform; one Marsaglia-Tsang candidate per coordinate
           uint32_t w0[4], w1[4], w2[4];
           philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 0, w0);
           philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 1, w1);
           philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 2, w2);
           double nrm[4];
-          box_muller_pair(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
-          box_muller_pair(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
+          fast_box_muller(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
+          if constexpr (K > 2) fast_box_muller(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
           const double ua[4] = {u32(w0[3]), u32(w1[3]), u32(w2[2]), u32(w2[3])};
-          uacc[v] = u53(w2[0], w2[1]);
+          uacc[v] = u52(w2[0], w2[1]);
           // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are
           // only generated by warps that contain such a function
           double ub[4] = {0.5, 0.5, 0.5, 0.5};
@@ -287,25 +362,21 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
 #pragma unroll
           for (int k = 0; k < K; k++) {
             const bool bo = sh[k] < 1.0;
-            const double she = bo ? sh[k] + 1.0 : sh[k];
-            const double lshe = bo ? log1p_small(sh[k]) : lsh[k];
-            const bool ok = gamma_candidate(she, lshe, nrm[k], ua[k], zp[v][k], lg[k]);
-            if (bo) {
-              const double lb = nl_log(ub[k]) / sh[k];
-              zp[v][k] *= exp(lb); lg[k] += lb;
-            }
+            const bool ok = gamma_candidate_fast(bo ? sh[k] + 1.0 : sh[k], nrm[k], ua[k], zp[v][k]);
+            if (bo) zp[v][k] *= nl_pow_u(ub[k], 1.0 / sh[k]);
             fast = fast && ok;
           }
         }
-        if (!fast) {          // a rejected candidate, K > 4 or padding: generic sampler
-          RngStream rs(a.key, gi, a.iteration, RNG_Z_PROPOSAL_SLOW);
+        if (!fast) {          // a rejected candidate or K > 4: generic sampler on its own stream
+          double tsh[K], tzp[K], tu = uacc[v];     // only these copies have their address taken
 #pragma unroll
-          for (int k = 0; k < K; k++) {
-            if (i0 + v < a.n) zp[v][k] = rs.gamma(sh[k], &lg[k]);
-            else { zp[v][k] = 1.0; lg[k] = 0.0; }
-          }
-          if (K > 4) uacc[v] = rs.uniform();
+          for (int k = 0; k < K; k++) tsh[k] = sh[k];
+          z_slow_proposal<K>(a.key, gi, a.iteration, tsh, tzp, &tu, live);
+#pragma unroll
+          for (int k = 0; k < K; k++) zp[v][k] = tzp[k];
+          uacc[v] = tu;
         }
+        double sum = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) sum += zp[v][k];
         if (a.draws_out) {
@@ -313,10 +384,9 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
           for (int k = 0; k < K; k++) a.draws_out[(size_t)k * a.ld + i0 + v] = zp[v][k];
           a.draws_out[(size_t)K * a.ld + i0 + v] = uacc[v];
         }
-        // log of the normalised proposal from the sampler's own log (one library log instead of K)
-        const double lsum = nl_log(sum);
+        const double rs = (sum > 1e-290 && sum < 1e290) ? fast_rcp(sum) : 1.0 / sum;
 #pragma unroll
-        for (int k = 0; k < K; k++) { zp[v][k] = zp[v][k] / sum; lzn[v][k] = lg[k] - lsum; }
+        for (int k = 0; k < K; k++) { zp[v][k] *= rs; lzn[v][k] = fast_log(zp[v][k]); }
       }
     }
     // ---- squared errors of the current and the proposed state
@@ -324,74 +394,89 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
 #pragma unroll
     for (int v = 0; v < V; v++) { so[v] = 0; sn[v] = 0; }
     Coef<K, M, COV, V> cf;
-    constexpr int NB = RG ? BWMAX : 0;
-    BandWin wo[V], wn[V];
+    if constexpr (!RG) {
+      const int QSc = COV ? a.QS : ((K * (M + 1) + 1) & ~1);      // compile-time without covariates
+      rows.run(a.P, [&](int p, const double (&c)[V]) {
+        cf.load(g + p * QSc, a.D, st.x);
 #pragma unroll
-    for (int v = 0; v < V; v++) { wo[v].clear(); wn[v].clear(); }
-    stream_rows<V, RG ? ROW_CH_RAGGED : ROW_CH, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
-                                                    [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
-      cf.load(g + p * a.QS, a.D, st.x);
+        for (int v = 0; v < V; v++) {
+          double ro = c[v], rn = c[v];
 #pragma unroll
-      for (int v = 0; v < V; v++) {
-        double ro = c[v], rn = c[v];
+          for (int k = 0; k < K; k++) {
+            double at = cf.get(v, k, 0);
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-          double at = cf.get(v, k, 0);
-#pragma unroll
-          for (int m = 0; m < M; m++) at = fma(st.chi[v][m], cf.get(v, k, m + 1), at);
-          ro = fma(-st.z[v][k], at, ro);
-          rn = fma(-zp[v][k], at, rn);
+            for (int m = 0; m < M; m++) at = fma(st.chi[v][m], cf.get(v, k, m + 1), at);
+            ro = fma(-st.z[v][k], at, ro);
+            rn = fma(-zp[v][k], at, rn);
+          }
+          so[v] = fma(ro, ro, so[v]);
+          sn[v] = fma(rn, rn, sn[v]);
         }
-        if constexpr (RG) {       // (c - theta)' G_i (c - theta) through the band of G_i
+      });
+    } else {
+      constexpr int NB = BWMAX;
+      BandWin wo[V], wn[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) { wo[v].clear(); wn[v].clear(); }
+      stream_rows<V, ROW_CH_RAGGED, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
+                                        [&](int p, const double (&c)[V], const double (&gb)[NB][V]) {
+        cf.load(g + p * a.QS, a.D, st.x);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          double ro = c[v], rn = c[v];
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            double at = cf.get(v, k, 0);
+#pragma unroll
+            for (int m = 0; m < M; m++) at = fma(st.chi[v][m], cf.get(v, k, m + 1), at);
+            ro = fma(-st.z[v][k], at, ro);
+            rn = fma(-zp[v][k], at, rn);
+          }
+          // (c - theta)' G_i (c - theta) through the band of G_i
           double gv[BWMAX];
 #pragma unroll
           for (int j = 0; j < BWMAX; j++) gv[j] = gb[j][v];
           so[v] += band_term_sq(gv, ro, wo[v]);
           sn[v] += band_term_sq(gv, rn, wn[v]);
           wo[v].push(ro); wn[v].push(rn);
-        } else {
-          so[v] = fma(ro, ro, so[v]);
-          sn[v] = fma(rn, rn, sn[v]);
         }
-      }
-    });
+      });
+    }
     // ---- acceptance
-    double znew[V][K];
+    double znew[V][K], lznew[V][K];
 #pragma unroll
     for (int v = 0; v < V; v++) {
-      double lp_old = 0, lp_new = 0;
+      double lp = 0;                 // lpdf(z*) - lpdf(z)
       bool nonpos = false;
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        lp_old += (a.alpha3 * a.pi[k] - 1) * lzo[v][k];
-        lp_new += (a.alpha3 * a.pi[k] - 1) * lzn[v][k];
+        lp = fma(a.alpha3 * a.pi[k] - 1, lzn[v][k] - lzo[v][k], lp);
         nonpos |= (st.z[v][k] <= 0);
       }
-      lp_old -= a.beta * (so[v] / (2 * a.sigma_sq));
-      lp_new -= a.beta * (sn[v] / (2 * a.sigma_sq));
+      lp = fma(-hb, sn[v] - so[v], lp);
       double q_new = 0, q_old = 0, lB_new = 0, lB_old = 0, tot_new = 0, tot_old = 0;
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        double al_from_old = a.a_Z_PM * st.z[v][k];   // parameters used to propose the new state
-        double al_from_new = a.a_Z_PM * zp[v][k];     // parameters of the reverse move
-        q_new += (al_from_old - 1) * lzn[v][k];
-        q_old += (al_from_new - 1) * lzo[v][k];
+        const double al_from_old = a.a_Z_PM * st.z[v][k];   // parameters used to propose the new state
+        const double al_from_new = a.a_Z_PM * zp[v][k];     // parameters of the reverse move
+        q_new = fma(al_from_old - 1, lzn[v][k], q_new);
+        q_old = fma(al_from_new - 1, lzo[v][k], q_old);
         // log(a * z) = log a + log z: both logs are already in registers
-        lB_new += lgamma_known_log(al_from_old, a.log_a_Z_PM + lzo[v][k]); tot_new += al_from_old;
-        lB_old += lgamma_known_log(al_from_new, a.log_a_Z_PM + lzn[v][k]); tot_old += al_from_new;
+        lB_new += lgamma_pos(al_from_old, a.log_a_Z_PM + lzo[v][k]); tot_new += al_from_old;
+        lB_old += lgamma_pos(al_from_new, a.log_a_Z_PM + lzn[v][k]); tot_old += al_from_new;
       }
-      // tot = a * sum_k z_k with sum_k z_k = 1 up to rounding: log(tot) = log a + log1p(tot/a - 1)
-      q_new -= (lB_new - lgamma_known_log(tot_new, a.log_a_Z_PM + log1p_small((tot_new - a.a_Z_PM) / a.a_Z_PM)));
-      q_old -= (lB_old - lgamma_known_log(tot_old, a.log_a_Z_PM + log1p_small((tot_old - a.a_Z_PM) / a.a_Z_PM)));
-      double acc = lp_new - lp_old + q_old - q_new;
+      q_new -= (lB_new - lgamma_near_a(tot_new, a));
+      q_old -= (lB_old - lgamma_near_a(tot_old, a));
+      double acc = lp + (q_old - q_new);
       if (nonpos) acc = 1;                           // UpdateMixedMembership.h:170-174
       const bool live = (i0 + v) < a.n;
-      const bool take = live && (nl_log(uacc[v]) < acc);
+      const bool take = live && (fast_log(uacc[v]) < acc);
       if (a.acc_out && live) a.acc_out[i0 + v] = acc;
 #pragma unroll
       for (int k = 0; k < K; k++) {
         znew[v][k] = take ? zp[v][k] : st.z[v][k];
-        if (live) red[k] += take ? lzn[v][k] : lzo[v][k];
+        lznew[v][k] = take ? lzn[v][k] : lzo[v][k];
+        if (live) red[k] += lznew[v][k];
       }
       if (take) red[K] += 1.0;
     }
@@ -402,6 +487,9 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
 #pragma unroll
         for (int v = 0; v < V; v++) t[v] = znew[v][k];
         stv<V>(a.Z + (size_t)k * a.ld + i0, t);
+#pragma unroll
+        for (int v = 0; v < V; v++) t[v] = lznew[v][k];
+        stv<V>(a.lZ + (size_t)k * a.ld + i0, t);
       }
     }
   }
@@ -416,8 +504,10 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) z_kernel(
 template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];
+  build_log_table();
   stage_globals(a, g);
   double red[1] = {0};
+  const double bs = a.beta / a.sigma_sq;
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);
@@ -500,7 +590,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
           uint32_t w[4];
           philox_words(a.key, gi, a.iteration, RNG_CHI, pr, w);
           double n0, n1;
-          box_muller_pair(w[0], w[1], w[2], n0, n1);
+          fast_box_muller(w[0], w[1], w[2], n0, n1);
           eps[v][2 * pr] = n0;
           if (2 * pr + 1 < M) eps[v][2 * pr + 1] = n1;
         }
@@ -525,10 +615,8 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
 #pragma unroll
         for (int q = 0; q < M; q++)
           if (q != m) w = fma(-(q < m ? G[v][q][m] : G[v][m][q]), st.chi[v][q], w);
-        w = (w * a.beta) / a.sigma_sq;
-        double W = 1 + ((G[v][m][m] * a.beta) / a.sigma_sq);
-        W = 1 / W;
-        st.chi[v][m] = W * w + sqrt(W) * eps[v][m];
+        const double W = fast_rcp(fma(G[v][m][m], bs, 1.0));        // 1 / (1 + beta G_mm / sigma^2) in (0, 1]
+        st.chi[v][m] = fma(W * bs, w, fast_sqrt(W) * eps[v][m]);
       }
       // residual sum of squares with the new chi: rss + |d|^2 - 2 chi'r + chi' G chi
       double quad = 0, lin = 0;
@@ -616,11 +704,14 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
 #endif
 
 template <int V, typename Kern>
-inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s) {
-  size_t smem = (size_t)a.P * a.QS * sizeof(double);
+inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extra_smem = 0) {
+  size_t smem = (size_t)a.P * a.QS * sizeof(double) + extra_smem;
   // resident blocks per SM of this instantiation (queried once), grid = one full wave
   static std::unordered_map<const void*, std::pair<size_t, int>> cache;   // kernel -> (smem, blocks per SM)
-  auto it = cache.find((const void*)kern);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const void* key = (const void*)((const char*)kern + dev);      // the attribute / occupancy are per device
+  auto it = cache.find(key);
   if (it == cache.end() || it->second.first != smem) {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -628,8 +719,8 @@ inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s) {
     }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PF_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
-    cache[(const void*)kern] = std::make_pair(smem, nb);
-    it = cache.find((const void*)kern);
+    cache[key] = std::make_pair(smem, nb);
+    it = cache.find(key);
   }
   const int per_sm = it->second.second;
   int need = pass_grid(a.ld, V);

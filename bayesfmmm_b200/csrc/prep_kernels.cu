@@ -43,6 +43,41 @@ int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots,
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ log Z cache
+// dst = log(src): the Z step keeps log Z next to Z (the logs of the current state are then read, not
+// recomputed, every iteration); this kernel initialises the cache when the caller sets Z.
+__global__ void __launch_bounds__(256) log_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = log(src[i]);
+}
+int launch_log_rows(const double* src, double* dst, size_t count, cudaStream_t s) {
+  if (count == 0) return 0;
+  size_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  log_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, count);
+  g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ statistics read-back without a copy engine
+// The sampler reads a few KB of reduced statistics two or three times per sweep.  As cudaMemcpyAsync
+// those reads queue on the device-to-host copy engine behind an overlapped 48 MB state transfer
+// (bfmmm_get_state_begin) and stall the sweep; stored by SM threads into mapped page-locked memory
+// they do not.  dst is the device alias of the host buffer.
+__global__ void __launch_bounds__(256) copy_to_host_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t len) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __ldcg(src + i);
+  __threadfence_system();
+}
+int launch_copy_to_host(const double* src, double* dst_mapped, int64_t len, cudaStream_t s) {
+  if (len <= 0) return 0;
+  int64_t blocks = (len + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  copy_to_host_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst_mapped, len);
+  g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ projection
 // c~_i = Q' y_i with Q = B L^{-T} (orthonormal columns), rss_i = ||y_i - Q c~_i||^2 evaluated
 // directly (not as ||y||^2 - ||c~||^2, which cancels catastrophically when sigma^2 << signal).

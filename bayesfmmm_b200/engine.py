@@ -124,6 +124,14 @@ class Engine:
         """D2H copy into caller-owned column-major buffers (the reference's chain slices)."""
         self._chk(self._lib.bfmmm_get_state(self._h, _p(Z), _p(chi)))
 
+    def get_state_begin(self, Z=None, chi=None):
+        """Starts an overlapped read-back of the current (Z, chi) into caller-owned column-major buffers
+        (page-locked for the copy to be asynchronous); later updates run while it is in flight."""
+        self._chk(self._lib.bfmmm_get_state_begin(self._h, _p(Z), _p(chi)))
+
+    def get_state_wait(self):
+        self._chk(self._lib.bfmmm_get_state_wait(self._h))
+
     def set_globals(self, nu, Phi, sigma_sq, eta=None, xi=None):
         nu, Phi = _f(nu), _f(Phi)
         eta_f = _f(eta) if eta is not None else None

@@ -258,14 +258,16 @@ def run_ours(a):
 
     # ---- e2e: the same sweep through the host-buffer API, copying the new Z and chi back into the
     # caller's chain storage every iteration (what the reference's chain containers require)
-    Zh = torch.empty((K, n), dtype=torch.float64).pin_memory().numpy().T      # column-major n x K view
-    Ch = torch.empty((M, n), dtype=torch.float64).pin_memory().numpy().T
+    # page-locked chain slots (two, used alternately: slice i travels while sweep i+1 runs)
+    slots = [(torch.empty((K, n), dtype=torch.float64).pin_memory().numpy().T,      # column-major n x K view
+              torch.empty((M, n), dtype=torch.float64).pin_memory().numpy().T) for _ in range(2)]
     _, stats_len = eng.stats_buffer()
 
     def e2e_steps(k):
-        for _ in range(k):
+        for it in range(k):
             smp.step(bf.SWEEP_FULL)
-            eng.get_state_into(Zh, Ch)
+            eng.get_state_begin(*slots[it % 2])
+        eng.get_state_wait()
     e2e_steps(2)
     e_steps = max(5, a.steps // 5)
     ms_e = timed(e2e_steps, e_steps)

@@ -73,6 +73,14 @@ int bfmmm_get_basis(bfmmm_engine* e, double* B_out);
 /* ---- per-observation state (replaces the Z / chi chain slices the updates read and write) --- */
 int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi);
 int bfmmm_get_state(bfmmm_engine* e, double* Z, double* chi);     /* either may be NULL */
+/* Overlapped read-back for drivers that keep every iteration's Z / chi slice (the reference's chain cubes,
+ * BFMMM.h:1253-1298 writes slice i+1 every iteration).  _begin snapshots the current (Z, chi) device-side,
+ * ordered after everything queued so far, and starts the device-to-host transfer on a separate copy
+ * stream into the caller's buffers (page-locked memory for the transfer to be asynchronous), so the
+ * next iteration's kernels run while the slice travels; it returns immediately.  _wait blocks until the
+ * last transfer started has landed.  A new _begin waits (on the device) for the previous transfer. */
+int bfmmm_get_state_begin(bfmmm_engine* e, double* Z, double* chi);   /* either may be NULL */
+int bfmmm_get_state_wait(bfmmm_engine* e);
 /* rows [i0, i0+count) only: Z count x K, chi count x M (column-major, leading dimension count) */
 int bfmmm_get_state_rows(bfmmm_engine* e, int64_t i0, int64_t count, double* Z, double* chi);
 

@@ -15,6 +15,10 @@ int bfmmm_debug_update_z_rng(bfmmm_engine* e, const double* pi, double alpha3, d
 int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out /* n x M */);
 /* the projected cache: whitened coefficients (n x P column-major) and orthogonal residual norms */
 int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss);
+/* the device routines of csrc/fastmath.cuh applied elementwise (host buffers): which = 0 log, 1 reciprocal,
+ * 2 sqrt, 3 log-Gamma, 4/5 cosine/sine of the circle point of a 32-bit word, 6 log1p series,
+ * 7 uniform from 52 bits, 8/9 the Box-Muller pair of three words derived from x */
+int bfmmm_debug_fastmath(int which, const double* x, double* y, int64_t n);
 #ifdef __cplusplus
 }
 #endif

@@ -207,3 +207,23 @@ def test_rank_deficient_basis(kind):
     Wm = np.concatenate([np.stack([Z[:, k]] + [Z[:, k] * chi[:, m] for m in range(M)], axis=1) for k in range(K)], axis=1)
     assert rel(R, (y @ B).T @ Wm) < 1e-9 and rel(eng.gram(), B.T @ B) < 1e-12
     eng.close()
+
+
+def test_overlapped_state_readback():
+    """bfmmm_get_state_begin / _wait return the state as of the call, even when updates are queued behind it."""
+    s = synth.functional_common(seed=77, n=1000, T=40, K=3, P=10, M=2)
+    eng = _mk(s)
+    n = s["n"]
+    Z1, c1 = np.zeros((n, 3), order="F"), np.zeros((n, 2), order="F")
+    Z2, c2 = np.zeros((n, 3), order="F"), np.zeros((n, 2), order="F")
+    eng.get_state_begin(Z1, c1)
+    eng.update_chi_async()                       # queued behind the snapshot: must not leak into slice 1
+    eng.update_z_async(s["pi"], 1.0, 1000.0)
+    eng.get_state_begin(Z2, c2)
+    eng.get_state_wait()
+    assert np.array_equal(Z1, s["Z"]) and np.array_equal(c1, s["chi"])
+    Zn, cn = eng.get_state()
+    assert np.array_equal(Z2, Zn) and np.array_equal(c2, cn)
+    assert not np.array_equal(c2, c1)
+    eng.get_state_wait()                         # idempotent
+    eng.close()

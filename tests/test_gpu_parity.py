@@ -141,7 +141,10 @@ def test_device_rng_replay(name):
     Zg, _ = eng.get_state(chi=False)
     Zo, acc_o, _ = orc.update_z(d, st, s["pi"], 1.3, cases.A_Z_PM, gam, u)
     decided = np.abs(np.log(u) - acc_o) > 1e-8
-    assert np.array_equal(Zg[decided], Zo[decided])
+    # same accept/reject decision everywhere; the device normalises with a reciprocal (last-bit differences)
+    took_g, took_o = np.any(Zg != s["Z"], axis=1), np.any(Zo != s["Z"], axis=1)
+    assert np.array_equal(took_g[decided], took_o[decided])
+    assert np.allclose(Zg[decided], Zo[decided], rtol=1e-15, atol=0)
     assert np.all((u > 0) & (u < 1)) and np.all(gam >= 0)     # tiny shapes may underflow to 0, as in R
     big = cases.A_Z_PM * s["Z"] > 5
     zscore = ((gam - cases.A_Z_PM * s["Z"]) / np.sqrt(cases.A_Z_PM * s["Z"]))[big]
