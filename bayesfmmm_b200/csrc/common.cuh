@@ -21,6 +21,7 @@ constexpr int RED_MAX = 8;      // values reduced per block in the per-function 
 
 struct PassArgs {
   int n, ld, P, D, QS;
+  int P4;                           // P rounded up to 4: the cache and the globals carry zero rows P..P4-1 (common grid)
   int sm_count, max_blocks;         // launch geometry: persistent grid of at most max_blocks blocks
   const double* __restrict__ Ct;    // common basis: whitened c~ ; ragged grids: least-squares c_i
   const double* __restrict__ Gl;    // ragged grids: lower band of G_i, row (j*P + p) = G_i[p-j][p]; else nullptr

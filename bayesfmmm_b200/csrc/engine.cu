@@ -31,6 +31,7 @@ constexpr int N_STAGE = 4;
 
 struct bfmmm_engine {
   int model = 0, n = 0, ld = 0, K = 0, P = 0, M = 0, D = 0, q = 0, QS = 0, device = 0;
+  int P4 = 0;   // P rounded up to a multiple of 4: allocated rows of Ct / glob (rows >= Pc stay zero)
   int Pc = 0;   // rows of the projected cache = rank of the basis Gram (= P unless the basis is rank deficient)
   int64_t T = 0;
   bool common = true, identity = false;
@@ -347,13 +348,14 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   } while (0)
   CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   const size_t ld = e->ld;
-  CUE(cudaMalloc(&e->Ct, ld * e->P * 8));
+  e->P4 = (e->P + 3) & ~3;
+  CUE(cudaMalloc(&e->Ct, ld * e->P4 * 8));
   CUE(cudaMalloc(&e->rss, ld * 8));
   CUE(cudaMalloc(&e->Z, ld * e->K * 8));
   CUE(cudaMalloc(&e->lZ, ld * e->K * 8));
   CUE(cudaMalloc(&e->chi, ld * e->M * 8));
   if (e->D) CUE(cudaMalloc(&e->X, ld * e->D * 8));
-  CUE(cudaMalloc(&e->glob, (size_t)e->P * e->QS * 8));
+  CUE(cudaMalloc(&e->glob, (size_t)e->P4 * e->QS * 8));
   CUE(cudaMalloc(&e->draws, ld * (std::max(e->K + 1, e->M)) * 8));
   e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q;
   if (e->ragged) e->stats_len += (int64_t)(e->q * (e->q + 1) / 2) * bf::BWMAX * e->P;   // upper bound (bw <= BWMAX)
@@ -364,7 +366,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMalloc(&e->st_partials, bf::stats_partial_doubles(e->P, e->q, e->st_blocks) * 8));
   CUE(cudaMalloc(&e->ticket, 4));
   CUE(cudaMemsetAsync(e->ticket, 0, 4, e->stream));
-  CUE(cudaMemsetAsync(e->Ct, 0, ld * e->P * 8, e->stream));
+  CUE(cudaMemsetAsync(e->Ct, 0, ld * e->P4 * 8, e->stream));
   CUE(cudaMemsetAsync(e->rss, 0, ld * 8, e->stream));
   CUE(cudaMemsetAsync(e->Z, 0, ld * e->K * 8, e->stream));
   if (bf::launch_log_rows(e->Z, e->lZ, ld * e->K, e->stream)) { fail("log kernel launch failed"); return bail(1); }
@@ -373,7 +375,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMemsetAsync(e->draws, 0, ld * (std::max(e->K + 1, e->M)) * 8, e->stream));
   if (e->D) CUE(cudaMemsetAsync(e->X, 0, ld * e->D * 8, e->stream));
   for (int i = 0; i < N_STAGE; i++) {
-    CUE(cudaMallocHost(&e->h_stage[i], (size_t)e->P * e->QS * 8));
+    CUE(cudaMallocHost(&e->h_stage[i], (size_t)e->P4 * e->QS * 8));
     CUE(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
   }
   CUE(cudaHostAlloc(&e->h_stats, e->stats_len * 8, cudaHostAllocMapped));
@@ -528,7 +530,8 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
   }
   for (int p = 0; p < e->Pc; p++)
     for (int f = e->q; f < QS; f++) h[(size_t)p * QS + f] = 0.0;
-  CU(cudaMemcpyAsync(e->glob, h, (size_t)e->Pc * QS * 8, cudaMemcpyHostToDevice, e->stream));
+  for (size_t idx = (size_t)e->Pc * QS; idx < (size_t)e->P4 * QS; idx++) h[idx] = 0.0;     // padding rows
+  CU(cudaMemcpyAsync(e->glob, h, (size_t)e->P4 * QS * 8, cudaMemcpyHostToDevice, e->stream));
   CU(cudaEventRecord(e->ev_stage[slot], e->stream));
   e->sigma_sq = sigma_sq;
   return 0;
@@ -536,7 +539,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
 
 static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
-  a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.D = e->D; a.QS = e->QS;
+  a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.D = e->D; a.QS = e->QS; a.P4 = (e->Pc + 3) & ~3;
   a.sm_count = e->sm_count; a.max_blocks = e->pass_blocks;
   a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.lZ = e->lZ; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
   a.sigma_sq = e->sigma_sq; a.beta = beta;

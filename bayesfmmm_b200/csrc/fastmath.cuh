@@ -138,9 +138,10 @@ __device__ __forceinline__ double stirling16(double x, double lx) {
   s = fma(r2, s, FM_STI[2]); s = fma(r2, s, FM_STI[1]); s = fma(r2, s, FM_STI[0]);
   return fma(x - 0.5, lx, -x) + fma(r, s, FM_STI[5]);
 }
-// log Gamma(x), x > 0, with lx = log x known.  x < 16 is shifted: Gamma(x) = Gamma(x + 16) / (x (x+1) ... (x+15)).
-__device__ __forceinline__ double lgamma_pos(double x, double lx) {
-  if (x >= 16.0) return stirling16(x, lx);
+// log Gamma(x), x > 0, with lx = log x known.  x < 16 is shifted: Gamma(x) = Gamma(x + 16) / (x (x+1) ... (x+15));
+// that branch is out of line (one copy per kernel instead of one per call site: the Z kernel is
+// instruction-cache sensitive).
+static __device__ __noinline__ double lgamma_shift16(double x, double lx) {
   double pr = (x + 1.0) * (x + 2.0);
 #pragma unroll
   for (int j = 3; j < 15; j += 2) pr *= fma(x, x + (2 * j + 1), (double)(j * (j + 1)));   // (x+j)(x+j+1)
@@ -148,6 +149,11 @@ __device__ __forceinline__ double lgamma_pos(double x, double lx) {
   const double xs = x + 16.0;
   return stirling16(xs, fast_log(xs)) - lx - fast_log(pr);
 }
+__device__ __forceinline__ double lgamma_pos(double x, double lx) {
+  if (x >= 16.0) return stirling16(x, lx);
+  return lgamma_shift16(x, lx);
+}
+static __device__ __noinline__ double fast_log_nl(double x) { return fast_log(x); }
 
 // One Marsaglia-Tsang candidate for shape >= 1 from a given normal x and accept-uniform uu.  Returns the
 // candidate g = d v and whether it is accepted (false with probability ~1e-3 at shape 10, ~1e-5 at
@@ -161,10 +167,10 @@ __device__ __forceinline__ bool gamma_candidate_fast(double shape, double x, dou
   const double v = v1 * v1 * v1;
   g = d * v;
   if (t <= -0.99) return false;
-  const double l3 = 3.0 * (fabs(t) <= 0.03125 ? log1p_series(t) : fast_log(v1));
+  const double l3 = 3.0 * (fabs(t) <= 0.03125 ? log1p_series(t) : fast_log_nl(v1));
   const double R = fma(0.5 * x, x, d * (1.0 - v + l3));
   bool ok = (uu - 1.0 < R);
-  if (!ok) ok = fast_log(uu) < R;
+  if (!ok) ok = fast_log_nl(uu) < R;
   return ok;
 }
 

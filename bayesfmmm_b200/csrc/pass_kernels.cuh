@@ -206,7 +206,7 @@ struct FnState {
 };
 
 __device__ __forceinline__ void stage_globals(const PassArgs& a, double* g) {
-  const int tot = a.P * a.QS;
+  const int tot = a.P4 * a.QS;
   for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) g[idx] = a.glob[idx];
   __syncthreads();
 }
@@ -221,41 +221,35 @@ __device__ __forceinline__ void stage_globals(const PassArgs& a, double* g) {
 
 // Rows of the coefficient cache in groups of four, two groups alternating (A is consumed while B is in
 // flight and vice versa: no register copies).  begin() issues the first group, so the caller can put
-// independent work (the proposal) between it and run().  P % 4 == 0 takes a predicate-free path.
+// independent work (the proposal) between it and run().  The cache and the globals are padded with
+// zero rows up to P4 = a multiple of four (they add nothing to any sum), so there are no predicates.
 template <int V>
 struct RowStream {
   double A[4][V], B[4][V];
   const double* q;
   size_t s1;
-  template <bool FULL>
-  __device__ __forceinline__ void fetch(const double* r, int p, int P, double (&c)[4][V]) {
+  __device__ __forceinline__ void fetch(const double* r, double (&c)[4][V]) {
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (FULL || p + j < P) ldv_cs<V>(r + j * s1, c[j]);
+    for (int j = 0; j < 4; j++) ldv_cs<V>(r + j * s1, c[j]);
   }
-  __device__ __forceinline__ void begin(const double* col, int ld, int P) {
+  __device__ __forceinline__ void begin(const double* col, int ld) {
     q = col; s1 = (size_t)ld;
-    if ((P & 3) == 0) fetch<true>(q, 0, P, A); else fetch<false>(q, 0, P, A);
-  }
-  template <bool FULL, typename F>
-  __device__ __forceinline__ void loop(int P, F&& body) {
-    for (int p = 0; p < P; p += 8) {
-      if (p + 4 < P) fetch<FULL>(q + 4 * s1, p + 4, P, B);
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (FULL || p + j < P) body(p + j, A[j]);
-      q += 8 * s1;
-      if (p + 8 < P) fetch<FULL>(q, p + 8, P, A);
-      if (p + 4 < P) {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (FULL || p + 4 + j < P) body(p + 4 + j, B[j]);
-      }
-    }
+    fetch(q, A);
   }
   template <typename F>
-  __device__ __forceinline__ void run(int P, F&& body) {
-    if ((P & 3) == 0) loop<true>(P, body); else loop<false>(P, body);
+  __device__ __forceinline__ void run(int P4, F&& body) {
+    for (int p = 0; p < P4; p += 8) {
+      const bool second = p + 4 < P4;
+      if (second) fetch(q + 4 * s1, B);
+#pragma unroll
+      for (int j = 0; j < 4; j++) body(p + j, A[j]);
+      q += 8 * s1;
+      if (p + 8 < P4) fetch(q, A);
+      if (second) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) body(p + 4 + j, B[j]);
+      }
+    }
   }
 };
 
@@ -275,7 +269,7 @@ static __device__ __noinline__ double nl_pow_u(double u, double inv_shape) { ret
 __device__ __forceinline__ double lgamma_near_a(double tot, const PassArgs& a) {
   const double dt = tot - a.a_Z_PM;
   if (fabs(dt) <= 1e-8 * a.a_Z_PM) return fma(dt, fma(0.5 * dt, a.trigam_a, a.digam_a), a.lgam_a);
-  return lgamma_pos(tot, fast_log(tot));
+  return lgamma_shift16(tot, fast_log_nl(tot));     // rows of Z that do not sum to one (rare): the shift is valid for any tot > 0
 }
 
 #ifndef BF_Z_MINB
@@ -295,7 +289,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
     FnState<K, M, COV, V> st;
     st.load(a, i0);
     RowStream<V> rows;
-    if constexpr (!RG) rows.begin(a.Ct + i0, a.ld, a.P);      // first rows in flight during the proposal
+    if constexpr (!RG) rows.begin(a.Ct + i0, a.ld);      // first rows in flight during the proposal
     double zp[V][K], uacc[V], lzo[V][K], lzn[V][K];
     {
       double t[V];
@@ -330,6 +324,22 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
         const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
         const bool live = (i0 + v) < a.n;
         bool fast = (K <= 4);
+        // The random words and the normals do not depend on the state: they are generated first, so the
+        // loads of Z, chi and log Z issued above are in flight for a few hundred instructions before their
+        // first use (they were 11 % of the kernel's stall samples when the shapes were computed first).
+        // Straight-line path: three Philox blocks give two Box-Muller pairs (4 normals), four 32-bit
+        // accept uniforms and the Metropolis uniform; one Marsaglia-Tsang candidate per coordinate.
+        double nrm[4] = {0, 0, 0, 0}, ua[4] = {0.5, 0.5, 0.5, 0.5};
+        if constexpr (K <= 4) {
+          uint32_t w0[4], w1[4], w2[4];
+          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 0, w0);
+          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 1, w1);
+          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 2, w2);
+          fast_box_muller(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
+          if constexpr (K > 2) fast_box_muller(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
+          ua[0] = u32(w0[3]); ua[1] = u32(w1[3]); ua[2] = u32(w2[2]); ua[3] = u32(w2[3]);
+          uacc[v] = u52(w2[0], w2[1]);
+        }
         bool small = false;
         double sh[K];
 #pragma unroll
@@ -339,17 +349,6 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
           small = small || (sh[k] < 1.0);
         }
         if constexpr (K <= 4) {
-          // straight-line path: three Philox blocks give two Box-Muller pairs (4 normals), four 32-bit
-          // accept uniforms and the Metropolis uniform; one Marsaglia-Tsang candidate per coordinate
-          uint32_t w0[4], w1[4], w2[4];
-          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 0, w0);
-          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 1, w1);
-          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 2, w2);
-          double nrm[4];
-          fast_box_muller(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
-          if constexpr (K > 2) fast_box_muller(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
-          const double ua[4] = {u32(w0[3]), u32(w1[3]), u32(w2[2]), u32(w2[3])};
-          uacc[v] = u52(w2[0], w2[1]);
           // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are
           // only generated by warps that contain such a function
           double ub[4] = {0.5, 0.5, 0.5, 0.5};
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
     Coef<K, M, COV, V> cf;
     if constexpr (!RG) {
       const int QSc = COV ? a.QS : ((K * (M + 1) + 1) & ~1);      // compile-time without covariates
-      rows.run(a.P, [&](int p, const double (&c)[V]) {
+      rows.run(a.P4, [&](int p, const double (&c)[V]) {
         cf.load(g + p * QSc, a.D, st.x);
 #pragma unroll
         for (int v = 0; v < V; v++) {
@@ -511,6 +510,26 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);
+    RowStream<V> rows;
+    if constexpr (!RG) rows.begin(a.Ct + i0, a.ld);
+    // the normals do not depend on the state: generated first, while the loads above are in flight
+    double eps[V][M];
+    if (!a.eps) {
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        // (M+1)/2 Box-Muller pairs, one Philox block each (three words used)
+        const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
+#pragma unroll
+        for (int pr = 0; pr < (M + 1) / 2; pr++) {
+          uint32_t w[4];
+          philox_words(a.key, gi, a.iteration, RNG_CHI, pr, w);
+          double n0, n1;
+          fast_box_muller(w[0], w[1], w[2], n0, n1);
+          eps[v][2 * pr] = n0;
+          if (2 * pr + 1 < M) eps[v][2 * pr + 1] = n1;
+        }
+      }
+    }
     double G[V][M][M], r[V][M], d0[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
@@ -531,8 +550,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
 #pragma unroll
       for (int m = 0; m < M; m++) wu[v][m].clear();
     }
-    stream_rows<V, RG ? ROW_CH_RAGGED : ROW_CH, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
-                                                    [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
+    auto body = [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
       for (int v = 0; v < V; v++) {
@@ -570,8 +588,13 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
           }
         }
       }
-    });
-    double eps[V][M];
+    };
+    if constexpr (RG) {
+      stream_rows<V, ROW_CH_RAGGED, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0, body);
+    } else {
+      const double nogb[1][V] = {};
+      rows.run(a.P4, [&](int p, const double (&c)[V]) { body(p, c, nogb); });
+    }
     if (a.eps) {
       double t[V];
 #pragma unroll
@@ -581,20 +604,6 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kerne
         for (int v = 0; v < V; v++) eps[v][m] = t[v];
       }
     } else {
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        // (M+1)/2 Box-Muller pairs, one Philox block each (three words used)
-        const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
-#pragma unroll
-        for (int pr = 0; pr < (M + 1) / 2; pr++) {
-          uint32_t w[4];
-          philox_words(a.key, gi, a.iteration, RNG_CHI, pr, w);
-          double n0, n1;
-          fast_box_muller(w[0], w[1], w[2], n0, n1);
-          eps[v][2 * pr] = n0;
-          if (2 * pr + 1 < M) eps[v][2 * pr + 1] = n1;
-        }
-      }
       if (a.draws_out) {
         double t[V];
 #pragma unroll
@@ -660,8 +669,7 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
     BandWin wr[V];
 #pragma unroll
     for (int v = 0; v < V; v++) wr[v].clear();
-    stream_rows<V, RG ? ROW_CH_RAGGED : ROW_CH, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0,
-                                                    [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
+    auto body = [&](int p, const double (&c)[V], const double (&gb)[NB > 0 ? NB : 1][V]) {
       cf.load(g + p * a.QS, a.D, st.x);
 #pragma unroll
       for (int v = 0; v < V; v++) {
@@ -683,7 +691,15 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
           acc[v] = fma(res, res, acc[v]);
         }
       }
-    });
+    };
+    if constexpr (RG) {
+      stream_rows<V, ROW_CH_RAGGED, NB>(a.Ct, a.Gl, a.bw, a.ld, a.P, i0, body);
+    } else {
+      const double nogb[1][V] = {};
+      RowStream<V> rows;
+      rows.begin(a.Ct + i0, a.ld);
+      rows.run(a.P4, [&](int p, const double (&c)[V]) { body(p, c, nogb); });
+    }
     double rssv[V];
     ldv<V>(a.rss + i0, rssv);
 #pragma unroll
@@ -705,7 +721,7 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
 
 template <int V, typename Kern>
 inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extra_smem = 0) {
-  size_t smem = (size_t)a.P * a.QS * sizeof(double) + extra_smem;
+  size_t smem = (size_t)a.P4 * a.QS * sizeof(double) + extra_smem;
   // resident blocks per SM of this instantiation (queried once), grid = one full wave
   static std::unordered_map<const void*, std::pair<size_t, int>> cache;   // kernel -> (smem, blocks per SM)
   int dev = 0;

@@ -1,2 +1,2 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python bench.py --steps 100 --warmup 10 > gpurun_out/bench_new.log 2>&1; tail -1 gpurun_out/bench_new.log
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python tools/kbench.py tv:BFMMM_V_CHI=1 tv:BFMMM_V_Z=2 tv:BFMMM_V_SSR=1
