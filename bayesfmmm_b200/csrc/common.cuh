@@ -10,6 +10,7 @@
 //                 f = ((k*(M+1) + m')*(1+D) + d'), m'=0 mean block / m'=m+1 eigen block m,
 //                 d'=0 plain / d'=d+1 covariate d; QS = q rounded up to 2.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -285,8 +286,14 @@ int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
 int pass_grid(int ld, int v);
 
+// TMA descriptors of the statistics kernel's operands (see stats_kernels.cu)
+struct alignas(64) StatsTmaMaps {
+  CUtensorMap ct, z, chi, x;
+  int valid, mt;
+};
 struct StatsArgs {
   int n, ld, P, K, M, D, q;
+  const StatsTmaMaps* tma;          // host pointer (passed to the kernel by value) or nullptr
   const double* __restrict__ Ct;
   const double* __restrict__ Z;
   const double* __restrict__ chi;
@@ -298,6 +305,8 @@ struct StatsArgs {
 };
 int launch_stats(const StatsArgs& a, cudaStream_t s);
 int stats_blocks(int sm_count);
+int stats_tma_setup(StatsTmaMaps* out, const double* Ct, const double* Z, const double* chi, const double* X,
+                    int ld, int P, int K, int M, int D, int q);
 size_t stats_partial_doubles(int P, int q, int blocks);
 
 struct ProjectArgs {

@@ -52,6 +52,7 @@ struct bfmmm_engine {
   double *draws = nullptr, *stats = nullptr, *partials = nullptr, *st_partials = nullptr, *acc_dbg = nullptr;
   unsigned int* ticket = nullptr;
   int64_t stats_len = 0;
+  bf::StatsTmaMaps tma;            // TMA descriptors of the statistics kernel (valid = 0: cp.async path)
   int pass_blocks = 0, st_blocks = 0;
   // host
   std::vector<double> B, G, L;       // basis T x P row-major, Gram P x P col-major, whitening matrix P x Pc col-major
@@ -402,6 +403,8 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     e->sum_half = (double)e->n * (double)(e->T / 2);             // sum_i floor(n_i / 2), UpdateSigma.h:49
   }
   if (e->D && upload_cols(e, e->X, c->X, e->D)) return bail(1);
+  e->tma.valid = 0;
+  if (!e->ragged) bf::stats_tma_setup(&e->tma, e->Ct, e->Z, e->chi, e->X, e->ld, e->Pc, e->K, e->M, e->D, e->q);
   CUE(cudaStreamSynchronize(e->stream));
 #undef CUE
   *out = e;
@@ -650,6 +653,7 @@ int bfmmm_suffstats_async(bfmmm_engine* e) {
   CU(cudaSetDevice(e->device));
   bf::StatsArgs a;
   a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.K = e->K; a.M = e->M; a.D = e->D; a.q = e->q;
+  a.tma = (!e->ragged && e->tma.valid) ? &e->tma : nullptr;
   a.Ct = e->ragged ? e->Hh : e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
   a.WtW = e->stats + e->off_wtw(); a.CtW = e->stats + e->off_ctw(); a.blocks = e->st_blocks;
   int rc = bf::launch_stats(a, e->stream);

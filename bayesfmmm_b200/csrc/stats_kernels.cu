@@ -26,6 +26,8 @@
 
 namespace bf {
 
+static inline void stats_shape(int P, int q, int& MT, int& NT, int& gy);
+
 constexpr int ST_THREADS = 256;
 constexpr int ST_WARPS = ST_THREADS / 32;
 
@@ -180,18 +182,23 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stats_kernel(const StatsArgs a)
 }
 
 // ------------------------------------------------------------------ TMA-fed variant
-// The same contraction with the operands staged by the TMA engine: a producer warp issues
-// cp.async.bulk (SASS UBLKCP) copies of 512-byte row segments (64 functions of one row of the cache,
-// of Z, chi or X) into a ring of shared-memory stages and signals an mbarrier with the byte count;
-// the eight consumer warps wait on the "full" barrier, read their DMMA fragments from shared memory
-// (row stride 576 B: the two rows touched by a quarter-warp fall into disjoint bank halves), and
-// release the stage through the "empty" barrier.  No thread holds operands in registers while they
-// are in flight and the loads need no LSU issue slots at all.
+// The same contraction with the operands staged by the TMA engine.  A producer warp issues, per stage
+// of 64 functions, ONE cp.async.bulk.tensor.2d (SASS UTMALDG) per operand -- the [8 MT rows x 72
+// functions] box of the coefficient cache, the K rows of Z, the M rows of chi, the D rows of X -- into a
+// ring of shared-memory stages and the TMA unit signals the stage's "full" mbarrier with the byte count;
+// the eight consumer warps wait on it, read their DMMA fragments from shared memory and release the
+// stage through the "empty" mbarrier.  No thread holds operands in registers while they are in flight
+// and the loads need no LSU issue slots.  The box is 72 functions wide although a stage consumes 64: the
+// 576-byte row pitch puts the two rows a quarter-warp touches into disjoint bank halves (a 512-byte
+// pitch would be a 2-way conflict on every fragment load; the 128-byte swizzle needs rows <= 128 B); the
+// 8 extra functions are the next stage's first (an L2 hit then).  Rows beyond P and functions beyond ld
+// are zero-filled by the TMA unit, so there are no bounds predicates.  (A first version issued one 1-D
+// bulk copy per ROW, 26 per stage: a single thread cannot issue them fast enough -- 84 us.)
 constexpr int TM_CONSUMERS = 8;                 // consumer warps
 constexpr int TM_THREADS = (TM_CONSUMERS + 1) * 32;
-constexpr int TM_FN = 64;                       // functions per stage (8 per consumer warp)
-constexpr int TM_ROWB = TM_FN * 8;              // 512 bytes copied per row
-constexpr int TM_STRIDE = TM_ROWB + 64;         // shared-memory row stride
+constexpr int TM_FN = 64;                       // functions consumed per stage (8 per consumer warp)
+constexpr int TM_BOX = 72;                      // functions copied per stage row
+constexpr int TM_STRIDE = TM_BOX * 8;           // shared-memory row pitch in bytes (576)
 constexpr int TM_STAGES = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -215,13 +222,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   }
   __trap();
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
+__host__ __device__ inline int tm_align128(int bytes) { return (bytes + 127) & ~127; }
+
 template <int MT, int NT>
-__global__ void __launch_bounds__(TM_THREADS, 1) stats_kernel_tma(const StatsArgs a) {
+__global__ void __launch_bounds__(TM_THREADS, 2) stats_kernel_tma(const StatsArgs a, const __grid_constant__ StatsTmaMaps tm) {
   constexpr int TILES = MT * NT + NT * NT;
   extern __shared__ __align__(128) unsigned char tm_smem[];
   __shared__ double s_acc[TILES * 64];
@@ -230,11 +239,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) stats_kernel_tma(const StatsArg
   const int g = lane >> 2, c = lane & 3;
   const int mt0 = blockIdx.y * MT;
   const bool do_wtw = (blockIdx.y == 0);
-  // rows of one stage: the P_blk rows of the cache this block needs, then Z (K), chi (M), X (D)
-  const int p_lo = mt0 * 8;
-  const int p_cnt = max(0, min(a.P - p_lo, MT * 8));
-  const int NR = p_cnt + a.K + a.M + a.D;
-  const size_t stage_bytes = (size_t)NR * TM_STRIDE;
+  // regions of one stage (each 128-byte aligned): MT*8 rows of the cache, then Z (K), chi (M), X (D)
+  const int off_z = tm_align128(MT * 8 * TM_STRIDE);
+  const int off_c = off_z + tm_align128(a.K * TM_STRIDE);
+  const int off_x = off_c + tm_align128(a.M * TM_STRIDE);
+  const int stage_bytes = off_x + tm_align128(a.D * TM_STRIDE);
+  const unsigned tx_bytes = (unsigned)((MT * 8 + a.K + a.M + a.D) * TM_STRIDE);
   if (threadIdx.x == 0) {
     for (int s = 0; s < TM_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TM_CONSUMERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -248,33 +258,29 @@ __global__ void __launch_bounds__(TM_THREADS, 1) stats_kernel_tma(const StatsArg
       for (int sc = blockIdx.x; sc < n_super; sc += gridDim.x, it++) {
         const int st = it % TM_STAGES;
         if (it >= TM_STAGES) mbar_wait(&empty_bar[st], ((it / TM_STAGES) - 1) & 1);
-        mbar_expect_tx(&full_bar[st], (unsigned)(NR * TM_ROWB));
+        mbar_expect_tx(&full_bar[st], tx_bytes);
         unsigned char* base = tm_smem + (size_t)st * stage_bytes;
-        const size_t col = (size_t)sc * TM_FN;
-        int r = 0;
-        for (int p = 0; p < p_cnt; p++, r++) bulk_g2s(base + (size_t)r * TM_STRIDE, a.Ct + (size_t)(p_lo + p) * a.ld + col, TM_ROWB, &full_bar[st]);
-        for (int k = 0; k < a.K; k++, r++) bulk_g2s(base + (size_t)r * TM_STRIDE, a.Z + (size_t)k * a.ld + col, TM_ROWB, &full_bar[st]);
-        for (int m = 0; m < a.M; m++, r++) bulk_g2s(base + (size_t)r * TM_STRIDE, a.chi + (size_t)m * a.ld + col, TM_ROWB, &full_bar[st]);
-        for (int d = 0; d < a.D; d++, r++) bulk_g2s(base + (size_t)r * TM_STRIDE, a.X + (size_t)d * a.ld + col, TM_ROWB, &full_bar[st]);
+        const int col = sc * TM_FN;
+        tma_load_2d(base, &tm.ct, col, mt0 * 8, &full_bar[st]);
+        tma_load_2d(base + off_z, &tm.z, col, 0, &full_bar[st]);
+        tma_load_2d(base + off_c, &tm.chi, col, 0, &full_bar[st]);
+        if (a.D > 0) tma_load_2d(base + off_x, &tm.x, col, 0, &full_bar[st]);
       }
     }
   } else {
     // ===== consumer warps =====
-    int zrow[NT], crow[NT], xrow[NT];       // stage rows of this thread's feature in each n-tile (-1: none)
+    int zoff[NT], coff_[NT], xoff[NT];       // byte offsets of this thread's feature rows in a stage (-1: none)
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) {
       int f = nt * 8 + g;
-      zrow[nt] = -1; crow[nt] = -1; xrow[nt] = -1;
+      zoff[nt] = -1; coff_[nt] = -1; xoff[nt] = -1;
       if (f < a.q) {
         int dd = f % (1 + a.D), km = f / (1 + a.D), mm = km % (a.M + 1), k = km / (a.M + 1);
-        zrow[nt] = p_cnt + k;
-        if (mm > 0) crow[nt] = p_cnt + a.K + (mm - 1);
-        if (dd > 0) xrow[nt] = p_cnt + a.K + a.M + (dd - 1);
+        zoff[nt] = off_z + k * TM_STRIDE;
+        if (mm > 0) coff_[nt] = off_c + (mm - 1) * TM_STRIDE;
+        if (dd > 0) xoff[nt] = off_x + (dd - 1) * TM_STRIDE;
       }
     }
-    int arow[MT];
-#pragma unroll
-    for (int mt = 0; mt < MT; mt++) { int p = mt * 8 + g; arow[mt] = (p < p_cnt) ? p : -1; }
     double R[MT][NT][2], S[NT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
@@ -292,15 +298,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) stats_kernel_tma(const StatsArg
       const unsigned char* base = tm_smem + (size_t)st * stage_bytes + coff;
       double2 av[MT], wv[NT];
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++)
-        av[mt] = arow[mt] >= 0 ? *reinterpret_cast<const double2*>(base + (size_t)arow[mt] * TM_STRIDE) : make_double2(0.0, 0.0);
+      for (int mt = 0; mt < MT; mt++)                 // rows >= P were zero-filled by the TMA unit
+        av[mt] = *reinterpret_cast<const double2*>(base + (size_t)(mt * 8 + g) * TM_STRIDE);
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) {
         double2 w = make_double2(0.0, 0.0);
-        if (zrow[nt] >= 0) {
-          w = *reinterpret_cast<const double2*>(base + (size_t)zrow[nt] * TM_STRIDE);
-          if (crow[nt] >= 0) { const double2 t = *reinterpret_cast<const double2*>(base + (size_t)crow[nt] * TM_STRIDE); w.x *= t.x; w.y *= t.y; }
-          if (xrow[nt] >= 0) { const double2 t = *reinterpret_cast<const double2*>(base + (size_t)xrow[nt] * TM_STRIDE); w.x *= t.x; w.y *= t.y; }
+        if (zoff[nt] >= 0) {
+          w = *reinterpret_cast<const double2*>(base + zoff[nt]);
+          if (coff_[nt] >= 0) { const double2 t = *reinterpret_cast<const double2*>(base + coff_[nt]); w.x *= t.x; w.y *= t.y; }
+          if (xoff[nt] >= 0) { const double2 t = *reinterpret_cast<const double2*>(base + xoff[nt]); w.x *= t.x; w.y *= t.y; }
         }
         wv[nt] = w;
       }
@@ -420,10 +426,12 @@ static int launch_stats_x(const StatsArgs& a, int gy, cudaStream_t s) {
 template <int MT, int NT>
 static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& used) {
   used = false;
-  static const bool disabled = std::getenv("BFMMM_STATS_TMA") == nullptr;   // opt-in: measured 84 us vs 56 us for the cp.async ring (n = 1e6)
-  const int NR = std::min(a.P, MT * 8) + a.K + a.M + a.D;
-  const size_t smem = (size_t)TM_STAGES * NR * TM_STRIDE;
-  if (disabled || smem > 200 * 1024 || (a.ld % TM_FN) != 0) return 0;
+  static const bool disabled = std::getenv("BFMMM_STATS_NO_TMA") != nullptr;
+  if (disabled || !a.tma || !a.tma->valid || a.tma->mt != MT || (a.ld % TM_FN) != 0) return 0;
+  const size_t stage = (size_t)tm_align128(MT * 8 * TM_STRIDE) + tm_align128(a.K * TM_STRIDE) + tm_align128(a.M * TM_STRIDE) +
+                       tm_align128(a.D * TM_STRIDE);
+  const size_t smem = (size_t)TM_STAGES * stage;
+  if (smem > 100 * 1024) return 0;                            // two blocks per SM
   int dev = 0;
   cudaGetDevice(&dev);
   static std::set<std::pair<int, size_t>> configured;       // per device: the attribute is per context
@@ -433,7 +441,7 @@ static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& us
     configured.insert({dev, smem});
   }
   dim3 grid(a.blocks, gy);
-  stats_kernel_tma<MT, NT><<<grid, TM_THREADS, smem, s>>>(a);
+  stats_kernel_tma<MT, NT><<<grid, TM_THREADS, smem, s>>>(a, *a.tma);
   used = true;
   return 0;
 }
@@ -449,6 +457,37 @@ static int launch_stats_t(const StatsArgs& a, int gy, cudaStream_t s) {
   stats_final_kernel<MT, NT><<<(tot + 7) / 8, 256, 0, s>>>(a, a.blocks);
   g_launch_count += 2;
   return (int)cudaGetLastError();
+}
+
+// Tensor maps of the four operands ([rows][ld] doubles, function index contiguous): box = 72 functions x
+// (8 MT | K | M | D) rows.  Encoded once per engine through the driver entry point (no libcuda link).
+int stats_tma_setup(StatsTmaMaps* out, const double* Ct, const double* Z, const double* chi, const double* X,
+                    int ld, int P, int K, int M, int D, int q) {
+  out->valid = 0;
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess)
+    return 1;
+  int MT, NT, gy;
+  stats_shape(P, q, MT, NT, gy);
+  auto enc = [&](CUtensorMap* m, const double* base, int rows, int box_rows) -> bool {
+    if (rows <= 0) return true;
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)TM_BOX, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    return ((encode_fn)fn)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!enc(&out->ct, Ct, P, MT * 8) || !enc(&out->z, Z, K, K) || !enc(&out->chi, chi, M, M) || !enc(&out->x, X, D, D)) return 1;
+  out->mt = MT;
+  out->valid = 1;
+  return 0;
 }
 
 int launch_stats(const StatsArgs& a, cudaStream_t s) {

@@ -1,2 +1,3 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools/kbench.py tv:BFMMM_V_CHI=1 tv:BFMMM_V_Z=2 tv:BFMMM_V_SSR=1
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 100 --warmup 10 > gpurun_out/bench_new.log 2>&1; tail -1 gpurun_out/bench_new.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], {k: round(v['ms']*1e3,1) for k,v in d['roofline']['kernels'].items()}, d['roofline']['frac'], d['cpu_baseline']['value'])"
