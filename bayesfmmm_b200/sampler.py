@@ -82,6 +82,12 @@ class Sampler:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.bfmmm_sampler_destroy(self._h)
             self._h = C.c_void_p()
+        if getattr(self, "_p2p", None) is not None and self._p2p.value:
+            self._lib.bfmmm_p2p_destroy(self._p2p)
+            self._p2p = C.c_void_p()
+        if getattr(self, "_nccl", None) is not None and self._nccl.value:
+            self._lib.bfmmm_nccl_destroy(self._nccl)
+            self._nccl = C.c_void_p()
 
     def __del__(self):
         try:
@@ -191,6 +197,40 @@ class Sampler:
                 return 1
         self._cb = ALLREDUCE_FN(_cb)
         self._chk(self._lib.bfmmm_sampler_set_allreduce(self._h, self._cb, None))
+
+    def enable_nccl(self, rank: int, world: int, exchange_id, libnccl_path: str | None = None):
+        """Installs the native NCCL all-reduce (csrc/nccl_hook.cu).  `exchange_id(id_bytes_or_None) -> bytes`
+        must return rank 0's 128-byte unique id on every rank (e.g. a torch.distributed broadcast)."""
+        if libnccl_path is None:
+            try:
+                import nvidia.nccl as _n
+                import os as _os
+                cand = _os.path.join(list(_n.__path__)[0], "lib", "libnccl.so.2")
+                libnccl_path = cand if _os.path.exists(cand) else None
+            except Exception:
+                libnccl_path = None
+        path = libnccl_path.encode() if libnccl_path else None
+        idb = None
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            self._chk(self._lib.bfmmm_nccl_unique_id(path, buf))
+            idb = buf.raw
+        idb = exchange_id(idb)
+        comm = C.c_void_p()
+        self._chk(self._lib.bfmmm_sampler_enable_nccl(self._h, path, idb, C.c_int(rank), C.c_int(world), C.byref(comm)))
+        self._nccl = comm
+
+    def enable_p2p(self, rank: int, world: int, cap: int, allgather):
+        """Installs the NVLink peer-memory all-reduce (csrc/p2p_hook.cu).  `allgather(bytes64) -> bytes`
+        returns the concatenation of every rank's 64-byte IPC handle in rank order; the caller adds a barrier
+        before the first sweep."""
+        ctx = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        self._chk(self._lib.bfmmm_p2p_create(C.c_int(rank), C.c_int(world), C.c_int64(cap), C.byref(ctx), buf))
+        handles = allgather(buf.raw)
+        assert len(handles) == 64 * world
+        self._p2p = ctx
+        self._chk(self._lib.bfmmm_sampler_enable_p2p(self._h, ctx, handles))
 
     # ------------------------------------------------------------------ injected draws + single updates
     def tape(self, values):

@@ -214,18 +214,39 @@ def run_ours(a):
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
 
     if world > 1:
-        class _Buf:   # zero-copy torch view of the engine's statistics buffer
-            def __init__(self, ptr, ln):
-                self.__cuda_array_interface__ = {"shape": (ln,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-        ptr, ln = eng.stats_buffer()
-        stats_t = torch.as_tensor(_Buf(ptr, ln), device=torch.device("cuda", local))
+        # native NCCL all-reduce of the statistics buffer on the engine's stream (csrc/nccl_hook.cu); rank 0's
+        # unique id travels through the torch.distributed process group.  BFMMM_PY_ALLREDUCE=1 selects the
+        # generic hook through torch.distributed instead (what a caller without NCCL handles would plug in).
+        if os.environ.get("BFMMM_PY_ALLREDUCE"):
+            class _Buf:   # zero-copy torch view of the engine's statistics buffer
+                def __init__(self, ptr, ln):
+                    self.__cuda_array_interface__ = {"shape": (ln,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+            ptr, ln = eng.stats_buffer()
+            stats_t = torch.as_tensor(_Buf(ptr, ln), device=torch.device("cuda", local))
+            torch.cuda.set_stream(ext)          # NCCL work is ordered on the engine's stream
 
-        torch.cuda.set_stream(ext)          # NCCL work is ordered on the engine's stream
-
-        def allreduce(p, l, stream):        # (device pointer, doubles): the whole buffer or one slot of it
-            off = (p - ptr) // 8
-            dist.all_reduce(stats_t[off:off + l])
-        smp.set_allreduce(allreduce)
+            def allreduce(p, l, stream):        # (device pointer, doubles): the whole buffer or one slot of it
+                off = (p - ptr) // 8
+                dist.all_reduce(stats_t[off:off + l])
+            smp.set_allreduce(allreduce)
+        elif not os.environ.get("BFMMM_P2P_ALLREDUCE"):
+            def exchange_id(idb):
+                t = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", local))
+                if rank == 0:
+                    t.copy_(torch.frombuffer(bytearray(idb), dtype=torch.uint8))
+                dist.broadcast(t, 0)
+                return bytes(t.cpu().numpy().tobytes())
+            smp.enable_nccl(rank, world, exchange_id)
+        else:
+            # BFMMM_P2P_ALLREDUCE=1: one-shot all-reduce over NVLink peer memory (csrc/p2p_hook.cu); the IPC handles
+            # of the mailboxes are all-gathered through the process group (measured equal to NCCL at 2 ranks)
+            def allgather(h):
+                mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).to(torch.device("cuda", local))
+                out = [torch.zeros(64, dtype=torch.uint8, device=torch.device("cuda", local)) for _ in range(world)]
+                dist.all_gather(out, mine)
+                return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+            smp.enable_p2p(rank, world, eng.stats_buffer()[1], allgather)
+            dist.barrier()
 
     def barrier():
         if world > 1:
@@ -308,7 +329,7 @@ def run_ours(a):
     g = smp.get()
     pi_now, a3 = g["pi"], g["alpha3"]
     kern = {
-        "z_kernel": (kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM)), n * (P + 2 * K + M) * 8),
+        "z_kernel": (kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM)), n * (P + 4 * K + M) * 8),   # Z and log Z read + written
         "chi_kernel": (kernel_ms(lambda: eng.update_chi_async()), n * (P + 1 + K + 2 * M) * 8),
         "ssr_kernel": (kernel_ms(lambda: eng.ssr_async()), n * (P + 1 + K + M) * 8),
         "stats_kernel": (kernel_ms(lambda: eng.suffstats_async()), n * (P + K + M) * 8),
@@ -327,7 +348,7 @@ def run_ours(a):
     try:   # dram bytes of the same kernel from the committed `ncu --set full` capture (profiles/), same n
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         if tr.get("n_per_gpu") == n:
-            traffic = tr["kernels"].get(dom)
+            traffic = tr["kernels"].get(dom, tr["kernels"].get(dom + "_tma"))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kinfo[dom]["gbs"], "peak": peak, "unit": "GB/s",
@@ -354,6 +375,7 @@ def run_ours(a):
             except Exception as exc:    # keep the GPU line even if the CPU checker cannot run
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {exc}"}
         print(json.dumps(out))
+    barrier()                 # no rank unmaps its peers' mailboxes while another is still exchanging
     smp.close(); eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -59,6 +59,22 @@ int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int
                                   bfmmm_sampler** out);
 void bfmmm_sampler_destroy(bfmmm_sampler* s);
 int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx);
+/* Native NCCL hook (csrc/nccl_hook.cu): ncclAllReduce on the engine's stream, no host-language round trip.
+ * libnccl is dlopen'ed (libnccl_path, or the library already mapped into the process when NULL).  Rank 0
+ * calls bfmmm_nccl_unique_id and distributes the 128 bytes; every rank then calls
+ * bfmmm_sampler_enable_nccl (a collective) with its CUDA device current. */
+int bfmmm_nccl_unique_id(const char* libnccl_path, char* id_out /* 128 bytes */);
+int bfmmm_sampler_enable_nccl(bfmmm_sampler* s, const char* libnccl_path, const char* id /* 128 bytes */, int rank,
+                              int world, void** comm_out);
+void bfmmm_nccl_destroy(void* comm);
+/* One-shot all-reduce over NVLink peer memory (csrc/p2p_hook.cu) for ranks of one node with peer access:
+ * every rank calls bfmmm_p2p_create (its mailbox + 64-byte CUDA IPC handle), the handles are all-gathered
+ * by the caller, then bfmmm_sampler_enable_p2p maps the peers and installs the hook.  Results are summed in
+ * rank order on every rank (bit-identical).  A barrier over all ranks must separate enable from the first
+ * sweep and the last sweep from bfmmm_p2p_destroy. */
+int bfmmm_p2p_create(int rank, int world, int64_t cap, void** ctx_out, char* handle_out /* 64 bytes */);
+int bfmmm_sampler_enable_p2p(bfmmm_sampler* s, void* ctx, const char* handles /* world x 64 bytes */);
+void bfmmm_p2p_destroy(void* ctx);
 /* ragged grids: the pair cross-Gram band (bfmmm_suffstats_ragged) used by the block draws that follow */
 int bfmmm_sampler_set_hband(bfmmm_sampler* s, const double* Hband);
 /* totals over all shards of sum_i floor(n_i/2) and sum_i n_i (defaults: this shard's counts scaled by n_total/n) */
