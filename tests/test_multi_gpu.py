@@ -32,7 +32,7 @@ def _summary(smp):
                            g["tau"], g["delta"].ravel()])
 
 
-def _worker(rank, world, port, q, n_sweeps):
+def _worker(rank, world, port, q, n_sweeps, hook="python"):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -51,16 +51,37 @@ def _worker(rank, world, port, q, n_sweeps):
         off = (p - ptr) // 8
         with torch.cuda.stream(ext):
             dist.all_reduce(t[off:off + l])
-    smp.set_allreduce(allreduce)
+    dev = torch.device("cuda", rank)
+    if hook == "python":            # generic hook through torch.distributed
+        smp.set_allreduce(allreduce)
+    elif hook == "nccl":            # native ncclAllReduce (csrc/nccl_hook.cu)
+        def exchange_id(idb):
+            tt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                tt.copy_(torch.frombuffer(bytearray(idb), dtype=torch.uint8))
+            dist.broadcast(tt, 0)
+            return bytes(tt.cpu().numpy().tobytes())
+        smp.enable_nccl(rank, world, exchange_id)
+    else:                           # one-shot all-reduce over NVLink peer memory (csrc/p2p_hook.cu)
+        def allgather(h):
+            mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).to(dev)
+            out = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(out, mine)
+            return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+        smp.enable_p2p(rank, world, ln, allgather)
+        dist.barrier()
     for _ in range(n_sweeps):
         smp.step(bf.SWEEP_FULL)
     Z, chi = eng.get_state()
     q.put((rank, _summary(smp), Z, chi, smp.last_accept))
+    dist.barrier()
+    torch.cuda.synchronize()
     smp.close(); eng.close()
     dist.destroy_process_group()
 
 
-def test_two_gpu_chain_follows_single_gpu_chain():
+@pytest.mark.parametrize("hook", ["python", "nccl", "p2p"])
+def test_two_gpu_chain_follows_single_gpu_chain(hook):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -71,7 +92,7 @@ def test_two_gpu_chain_follows_single_gpu_chain():
         port = sk.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, n_sweeps)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, n_sweeps, hook)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda r: r[0])
