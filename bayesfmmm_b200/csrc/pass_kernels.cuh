@@ -501,7 +501,10 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
 // space), then the reference's sequential m = 0..M-1 sweep is run on them, so chi(i,n) for n < m
 // is the already-updated value exactly as in UpdateChi.h:48.
 template <int K, int M, bool COV, int V, bool RG>
-__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : 4) chi_kernel(const PassArgs a) {
+#ifndef BF_CHI_MINB
+#define BF_CHI_MINB 4      // resident blocks per SM targeted by the V = 2 chi kernel (5 and 6 measured slower: spills)
+#endif
+__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : (RG ? 4 : BF_CHI_MINB)) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];
   build_log_table();
   stage_globals(a, g);

@@ -189,7 +189,7 @@ def run_ours(a):
     import torch.distributed as dist
     import bayesfmmm_b200 as bf
     from bayesfmmm_b200.engine import FUNCTIONAL
-    from oracle import oracle as orc   # penalty matrix helper only (host setup, outside the timed region)
+    from bayesfmmm_b200 import basis as bfbasis
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,7 +208,7 @@ def run_ours(a):
     del dat["y"]
     eng.set_state(dat["Z"], dat["chi"])
     hyper = bf.default_hyper(True)
-    smp = bf.Sampler(eng, hyper=hyper, n_total=n * world, Pmat=orc.pmat_rw1(P), seed=2024)
+    smp = bf.Sampler(eng, hyper=hyper, n_total=n * world, Pmat=bfbasis.pmat_rw1(P), seed=2024)
     par = dat["par"]
     smp.set(nu=par["nu"], Phi=par["Phi"], sigma_sq=0.01, pi=dat["pi"], alpha3=1.0)
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))

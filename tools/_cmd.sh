@@ -1,1 +1,1 @@
-timeout 800 python -m pytest tests/test_multi_gpu.py -x -q 2>&1 | tail -5
+python tools/kbench.py small c5 c6
