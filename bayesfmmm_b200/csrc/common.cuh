@@ -34,6 +34,7 @@ struct PassArgs {
   const double* __restrict__ X;
   const double* __restrict__ glob;
   double sigma_sq, beta;
+  const double* __restrict__ sigma_dev;   // chi: sigma^2 drawn on the device by sigma_draw_kernel (nullptr: use sigma_sq)
   // Z step
   double alpha3, a_Z_PM, log_a_Z_PM;
   double lgam_a, digam_a, trigam_a; // log Gamma, digamma, trigamma at a_Z_PM (host): lgamma(a sum_k z_k) by its Taylor series
@@ -345,6 +346,8 @@ int launch_band_width(const double* B, int64_t rows, int P, int* bw_dev, cudaStr
 int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots, int degree, int P,
                    double* B_rowmajor, cudaStream_t s);
 int launch_copy_to_host(const double* src, double* dst_mapped, int64_t len, cudaStream_t s);   // SM-driven D2H of a few KB
+int launch_sigma_draw(const double* ssr_dev, double a, double scale_ssr, double beta0, uint64_t key, uint64_t iteration,
+                      uint32_t purpose, double* sigma_dev, double* host_mapped, double seq, cudaStream_t s);
 int launch_log_rows(const double* src, double* dst, size_t count, cudaStream_t s);   // dst = log(src), elementwise
 
 extern unsigned long long g_launch_count;

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,6 +63,9 @@ struct bfmmm_engine {
   int stage_next = 0;
   double* h_stats = nullptr;
   double* h_stats_dev = nullptr;   // device alias of h_stats (mapped page-locked memory)
+  double *sigma_dev = nullptr, *h_sig = nullptr, *h_sig_dev = nullptr;   // device-drawn sigma^2; mapped {SSR, sigma^2, seq}
+  double sig_seq = 0;
+  bool sigma_armed = false;        // the next chi kernel reads sigma^2 from sigma_dev
   double sigma_sq = 1.0;
   uint64_t key = 0x9E3779B97F4A7C15ull, iteration = 0;
   // offsets into stats
@@ -109,6 +113,8 @@ void free_all(bfmmm_engine* e) {
     if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
   }
   if (e->h_stats) cudaFreeHost(e->h_stats);
+  if (e->h_sig) cudaFreeHost(e->h_sig);
+  cudaFree(e->sigma_dev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -381,6 +387,10 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   }
   CUE(cudaHostAlloc(&e->h_stats, e->stats_len * 8, cudaHostAllocMapped));
   CUE(cudaHostGetDevicePointer(&e->h_stats_dev, e->h_stats, 0));
+  CUE(cudaHostAlloc(&e->h_sig, 4 * 8, cudaHostAllocMapped));
+  CUE(cudaHostGetDevicePointer(&e->h_sig_dev, e->h_sig, 0));
+  e->h_sig[0] = e->h_sig[1] = e->h_sig[2] = e->h_sig[3] = 0;
+  CUE(cudaMalloc(&e->sigma_dev, 8));
   if (e->identity) {
     e->G.assign((size_t)e->P * e->P, 0.0);
     e->L.assign((size_t)e->P * e->P, 0.0);
@@ -606,6 +616,7 @@ int bfmmm_update_z(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_
 static int chi_launch(bfmmm_engine* e, double beta, bool injected) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
+  if (e->sigma_armed) { a.sigma_dev = e->sigma_dev; e->sigma_armed = false; }
   if (injected) a.eps = e->draws;
   a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
   int rc = e->ragged ? bf::launch_chi_ragged(a, e->K, e->M, e->stream) : bf::launch_chi(a, e->K, e->M, e->stream);
@@ -645,6 +656,36 @@ int bfmmm_ssr(bfmmm_engine* e, double* ssr, double* sum_half, double* n_points) 
   if (ssr) *ssr = e->h_stats[0];
   if (sum_half) *sum_half = e->sum_half;
   if (n_points) *n_points = e->n_points;
+  return 0;
+}
+
+// sigma^2 drawn on the device behind the SSR pass (see sigma_draw_kernel); arms the next chi launch
+int bfmmm_sigma_draw_async(bfmmm_engine* e, double a, double scale_ssr, double beta0, uint64_t key, uint64_t iteration,
+                           uint32_t purpose) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  e->sig_seq += 1.0;
+  if (bf::launch_sigma_draw(e->stats + e->off_ssr(), a, scale_ssr, beta0, key, iteration, purpose, e->sigma_dev, e->h_sig_dev,
+                            e->sig_seq, e->stream))
+    return fail("sigma kernel launch failed");
+  e->sigma_armed = true;
+  return 0;
+}
+// waits (polling the mapped sequence number, not the stream: later kernels may already be queued) for the
+// device draw and returns SSR and sigma^2; sigma^2 becomes the engine's value for the launches that follow
+int bfmmm_sigma_wait(bfmmm_engine* e, double* ssr, double* sigma_sq) {
+  if (!e) return fail("null engine");
+  volatile double* h = e->h_sig;
+  for (long long spin = 0; h[2] != e->sig_seq; spin++) {
+    if ((spin & 0xfffff) == 0xfffff && cudaStreamQuery(e->stream) != cudaErrorNotReady && h[2] != e->sig_seq) {
+      cudaError_t err = cudaGetLastError();
+      return fail(std::string("bfmmm_sigma_wait: the device draw did not arrive: ") + cudaGetErrorString(err));
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (ssr) *ssr = h[0];
+  if (sigma_sq) *sigma_sq = h[1];
+  e->sigma_sq = h[1];
   return 0;
 }
 

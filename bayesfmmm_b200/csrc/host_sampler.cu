@@ -1023,6 +1023,19 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   if (rc_blocks) return 1;
   if (push_globals(s)) return 1;
   if (bfmmm_ssr_async(e)) return 1;                        // updateSigma's data pass, new globals
+  // Fused path (no injected draws, no covariates): sigma^2 is drawn ON THE DEVICE right behind the SSR pass
+  // -- same Philox stream (key, iteration, HP_SIGMA), same Marsaglia-Tsang sampler as the host draw -- and the
+  // chi kernel is queued immediately behind it, so the device does not idle for a host round trip between
+  // the two passes.  The host takes (SSR, sigma^2) from mapped memory when it needs them.
+  const bool fused_sigma = do_chi && !s->D && !s->rng.use_tape && !std::getenv("BFMMM_NO_FUSED_SIGMA");
+  if (fused_sigma) {
+    double* dev = nullptr; int64_t len = 0;
+    if (bfmmm_stats_buffer_dev(e, &dev, &len)) return 1;
+    if (s->allreduce && s->allreduce(s->allreduce_ctx, dev + s->K + 1, 1, bfmmm_stream(e))) return sfail("all-reduce hook failed");
+    const double a_sh = tempered ? (beta * s->n_points_total) / 2 + s->h.alpha_0 : s->sum_half_total + s->h.alpha_0;
+    if (bfmmm_sigma_draw_async(e, a_sh, tempered ? beta / 2 : 0.5, s->h.beta_0, s->rng.key, s->rng.iteration, HP_SIGMA)) return 1;
+    if (bfmmm_update_chi_async(e, beta)) return 1;
+  }
   if (do_z) {                                              // updatePi_PM -> updateAlpha3
     if (bfmmm_host_update_pi(s, st_slz(s))) return 1;
     if (bfmmm_host_update_alpha3(s, st_slz(s))) return 1;
@@ -1033,13 +1046,25 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
     if (bfmmm_host_update_gamma(s)) return 1;
   }
   if (bfmmm_host_update_tau(s)) return 1;                  // updateTau (all three loops call it)
-  if (reduce_and_read(s, /*only_ssr=*/true)) return 1;
-  if (bfmmm_host_update_sigma(s, st_ssr(s), beta, tempered)) return 1;
-  double ssr_ll = st_ssr(s);
+  double ssr_ll;
+  if (fused_sigma) {
+    struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
+    double ssr_now = 0, sig_now = 0;
+    if (bfmmm_sigma_wait(e, &ssr_now, &sig_now)) return 1;
+    s->sigma_sq = sig_now;
+    if ((int64_t)s->stats.size() > s->K + 1) s->stats[s->K + 1] = ssr_now;
+    ssr_ll = ssr_now;
+  } else {
+    if (reduce_and_read(s, /*only_ssr=*/true)) return 1;
+    if (bfmmm_host_update_sigma(s, st_ssr(s), beta, tempered)) return 1;
+    ssr_ll = st_ssr(s);
+  }
   bool defer = false;
   if (do_chi) {                                            // updateChi (+ the SSR calcLikelihood needs)
-    if (push_globals(s)) return 1;
-    if (bfmmm_update_chi_async(e, beta)) return 1;
+    if (!fused_sigma) {
+      if (push_globals(s)) return 1;
+      if (bfmmm_update_chi_async(e, beta)) return 1;
+    }
     if (!s->D) {
       if (s->in_tt) {                                      // a tempered transition needs every slot's SSR now
         s->ll_pending = true; s->ll_sigma = s->sigma_sq;

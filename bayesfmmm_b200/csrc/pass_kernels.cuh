@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : (RG ? 4 : BF
   build_log_table();
   stage_globals(a, g);
   double red[1] = {0};
-  const double bs = a.beta / a.sigma_sq;
+  const double bs = a.beta / (a.sigma_dev ? *a.sigma_dev : a.sigma_sq);
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
     st.load(a, i0);

@@ -78,6 +78,33 @@ int launch_copy_to_host(const double* src, double* dst_mapped, int64_t len, cuda
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ sigma^2 on the device
+// updateSigma's draw (UpdateSigma.h:47-53; tempered :98-107): sigma^2 = 1 / ((1 / b1) Gamma(a)),
+// b1 = scale * SSR + beta_0, from the Philox stream (key, 0xB200, iteration, purpose) -- the stream and the
+// sampler (RngStream::gamma) the host-side draw uses.  One thread, right behind the SSR pass (and its
+// all-reduce): the chi kernel that follows reads sigma^2 from device memory, so the sweep does not wait
+// for a host round trip between the two passes.  (SSR, sigma^2) reach the host through mapped
+// page-locked memory; the sequence number is stored last.
+__global__ void sigma_draw_kernel(const double* __restrict__ ssr_dev, double a, double scale_ssr, double beta0, uint64_t key,
+                                  uint64_t iteration, uint32_t purpose, double* __restrict__ sigma_dev,
+                                  volatile double* host, double seq) {
+  RngStream rs(key, 0xB200ull, iteration, purpose);
+  const double ssr = *ssr_dev;
+  const double b1 = scale_ssr * ssr + beta0;
+  const double r = (1 / b1) * rs.gamma(a);
+  const double sig = 1 / r;
+  *sigma_dev = sig;
+  host[0] = ssr; host[1] = sig;
+  __threadfence_system();
+  host[2] = seq;
+}
+int launch_sigma_draw(const double* ssr_dev, double a, double scale_ssr, double beta0, uint64_t key, uint64_t iteration,
+                      uint32_t purpose, double* sigma_dev, double* host_mapped, double seq, cudaStream_t s) {
+  sigma_draw_kernel<<<1, 1, 0, s>>>(ssr_dev, a, scale_ssr, beta0, key, iteration, purpose, sigma_dev, host_mapped, seq);
+  g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ projection
 // c~_i = Q' y_i with Q = B L^{-T} (orthonormal columns), rss_i = ||y_i - Q c~_i||^2 evaluated
 // directly (not as ||y||^2 - ||c~||^2, which cancels catastrophically when sigma^2 << signal).

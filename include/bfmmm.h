@@ -84,6 +84,15 @@ int bfmmm_get_state_wait(bfmmm_engine* e);
 /* rows [i0, i0+count) only: Z count x K, chi count x M (column-major, leading dimension count) */
 int bfmmm_get_state_rows(bfmmm_engine* e, int64_t i0, int64_t count, double* Z, double* chi);
 
+/* sigma^2 drawn on the device right behind bfmmm_ssr_async (and the caller's all-reduce of the SSR slot):
+ * sigma^2 = 1 / ((1/b1) Gamma(a)), b1 = scale_ssr * SSR + beta_0 (UpdateSigma.h:47-53, tempered :98-107), from
+ * the counter-based stream (key, iteration, purpose).  The next bfmmm_update_chi_async reads it from device
+ * memory, so no host round trip separates the SSR pass from the chi pass; bfmmm_sigma_wait returns
+ * (SSR, sigma^2) as soon as the draw has happened (it does not wait for kernels queued behind it). */
+int bfmmm_sigma_draw_async(bfmmm_engine* e, double a, double scale_ssr, double beta0, uint64_t key,
+                           uint64_t iteration, uint32_t purpose);
+int bfmmm_sigma_wait(bfmmm_engine* e, double* ssr, double* sigma_sq);
+
 /* device-side snapshot / restore of (Z, chi): a rejected tempered transition keeps the
  * pre-transition slice (BFMMM.h:1631-1651) */
 int bfmmm_state_snapshot(bfmmm_engine* e);

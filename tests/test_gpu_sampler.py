@@ -249,3 +249,28 @@ def test_multivariate_matches_reference_stored_chain():
     lo, mid, hi = S["Multivariate_sigma_q"]
     assert lo * 0.6 < med < hi * 1.6, (med, lo, hi)     # n*R = 200 observations: a wide posterior
     smp.close(); eng.close()
+
+
+def test_device_sigma_draw_is_the_host_draw():
+    """The fused path draws sigma^2 on the device behind the SSR pass (bfmmm_sigma_draw_async) from the stream and
+    sampler of the host draw: the two chains coincide (libdevice vs libm rounding only)."""
+    out = {}
+    for mode in ("fused", "host"):
+        if mode == "host":
+            os.environ["BFMMM_NO_FUSED_SIGMA"] = "1"
+        try:
+            s, eng, smp = _functional(seed=9, n=500)
+            chain = []
+            for _ in range(5):
+                smp.step(bf.SWEEP_FULL)
+                g = smp.get()
+                chain.append([g["sigma_sq"], g["loglik"], *g["nu"].ravel(), *g["pi"]])
+            Z, chi = eng.get_state()
+            out[mode] = (np.array(chain), Z, chi)
+            smp.close(); eng.close()
+        finally:
+            os.environ.pop("BFMMM_NO_FUSED_SIGMA", None)
+    a, b = out["fused"], out["host"]
+    assert np.max(np.abs(a[0][0] - b[0][0]) / np.abs(b[0][0])) < 1e-12      # first sweep: identical up to rounding
+    assert np.max(np.abs(a[0] - b[0]) / (1e-3 + np.abs(b[0]))) < 1e-6        # five sweeps later still the same chain
+    assert np.mean(np.all(np.abs(a[1] - b[1]) < 1e-9, axis=1)) > 0.99

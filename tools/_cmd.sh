@@ -1,1 +1,1 @@
-python tools/kbench.py small c5 c6
+timeout 600 python -m pytest tests/test_gpu_sampler.py -x -q -k "device_sigma" 2>&1 | tail -8
