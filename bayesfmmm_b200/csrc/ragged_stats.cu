@@ -17,6 +17,7 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MTB = 2;     // m-tiles (16 band rows) per block
 constexpr int RS_QMAX = 40;
+constexpr int RS_BASEMAX = 16;  // K + M + D <= 6 + 6 + 4
 
 __device__ __forceinline__ void dmma884r(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -25,10 +26,12 @@ __device__ __forceinline__ void dmma884r(double& d0, double& d1, double a, doubl
 }
 
 template <int NTB>
-__global__ void __launch_bounds__(RS_THREADS) ragged_stats_kernel(const RaggedStatsArgs a) {
+__global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const RaggedStatsArgs a) {
   constexpr int TILES = RS_MTB * NTB;
   __shared__ double s_acc[TILES * 64];
   __shared__ double s_w[RS_WARPS][RS_QMAX][8];
+  __shared__ double s_base[RS_WARPS][RS_BASEMAX][8];
+  __shared__ uchar4 s_feat[RS_QMAX];          // feature -> rows of s_base: (Z row, chi row or 255, X row or 255)
   __shared__ unsigned char s_pa[NTB * 8], s_pb[NTB * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, c = lane & 3;
@@ -45,6 +48,13 @@ __global__ void __launch_bounds__(RS_THREADS) ragged_stats_kernel(const RaggedSt
     }
     s_pa[threadIdx.x] = pa; s_pb[threadIdx.x] = pb;
   }
+  if (threadIdx.x < a.q) {
+    const int f = threadIdx.x;
+    const int dd = f % (1 + a.D), km = f / (1 + a.D), mm = km % (a.M + 1), k = km / (a.M + 1);
+    s_feat[f] = make_uchar4((unsigned char)k, mm > 0 ? (unsigned char)(a.K + mm - 1) : 255,
+                            dd > 0 ? (unsigned char)(a.K + a.M + dd - 1) : 255, 0);
+  }
+  const int nbase = a.K + a.M + a.D;
   __syncthreads();
   const double* ap[RS_MTB];
 #pragma unroll
@@ -71,12 +81,19 @@ __global__ void __launch_bounds__(RS_THREADS) ragged_stats_kernel(const RaggedSt
 #pragma unroll
     for (int mt = 0; mt < RS_MTB; mt++)
       av[mt] = ap[mt] ? __ldcs(reinterpret_cast<const double2*>(ap[mt] + i8 + 2 * c)) : make_double2(0.0, 0.0);
-    // feature weights of the 8 functions of this chunk: w[f][slot]
+    // feature weights of the 8 functions of this chunk: w[f][slot].  The K + M + D base rows are staged
+    // once (two loads per lane), the products are formed from shared memory with the feature -> (k, m, d)
+    // table built at block start (no integer division in the loop).
+    for (int r = lane >> 3; r < nbase; r += 4) {
+      const double* src = r < a.K ? a.Z + (size_t)r * a.ld : (r < a.K + a.M ? a.chi + (size_t)(r - a.K) * a.ld : a.X + (size_t)(r - a.K - a.M) * a.ld);
+      s_base[warp][r][slot] = src[i8 + slot];
+    }
+    __syncwarp();
     for (int f = lane >> 3; f < a.q; f += 4) {
-      int dd = f % (1 + a.D), km = f / (1 + a.D), mm = km % (a.M + 1), k = km / (a.M + 1);
-      double w = a.Z[(size_t)k * a.ld + i8 + slot];
-      if (mm > 0) w *= a.chi[(size_t)(mm - 1) * a.ld + i8 + slot];
-      if (dd > 0) w *= a.X[(size_t)(dd - 1) * a.ld + i8 + slot];
+      const uchar4 t = s_feat[f];
+      double w = s_base[warp][t.x][slot];
+      if (t.y != 255) w *= s_base[warp][t.y][slot];
+      if (t.z != 255) w *= s_base[warp][t.z][slot];
       s_w[warp][f][slot] = w;
     }
     __syncwarp();
@@ -140,7 +157,7 @@ static void rs_shape(int P, int bw, int q, int sm_count, int& NTB, int& gx, int&
   gz = (ptiles + NTB - 1) / NTB;
   int mtiles = (bw * P + 7) / 8;
   gy = (mtiles + RS_MTB - 1) / RS_MTB;
-  gx = (2 * sm_count + gy * gz - 1) / (gy * gz);
+  gx = (2 * sm_count) / (gy * gz);       // two blocks per SM, ONE wave (rounding up left a 6 % second wave: 2x the time)
   if (gx < 1) gx = 1;
 }
 

@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_sampler.py -x -q -k "device_sigma" 2>&1 | tail -8
+timeout 900 python -m pytest tests -m gpu -x -q -k "ragged or cov or Ragged" 2>&1 | tail -3
+timeout 900 python tools/configs_bench.py c4 2>&1 | tail -1 | cut -c1-250
