@@ -32,6 +32,7 @@ constexpr int N_STAGE = 4;
 
 struct bfmmm_engine {
   int model = 0, n = 0, ld = 0, K = 0, P = 0, M = 0, D = 0, q = 0, QS = 0, device = 0;
+  int hbL = 0;  // lower bandwidth of the whitening factor L (B-spline Gram: banded), used by the whitening loops
   int P4 = 0;   // P rounded up to a multiple of 4: allocated rows of Ct / glob (rows >= Pc stay zero)
   int Pc = 0;   // rows of the projected cache = rank of the basis Gram (= P unless the basis is rank deficient)
   int64_t T = 0;
@@ -408,6 +409,14 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     e->stats_len = e->K + 3 + (int64_t)e->q * e->q + (int64_t)e->P * e->q + (int64_t)e->npairs * e->bw * e->P;
   } else {
     if (build_basis(e, c)) return bail(1);
+    e->hbL = e->P - 1;
+    if (e->Pc == e->P) {                       // Cholesky factor of a banded Gram matrix: same band
+      int hb = 0;
+      for (int p = 0; p < e->P; p++)
+        for (int r = p; r < e->P; r++)
+          if (e->L[(size_t)p * e->P + r] != 0.0 && r - p > hb) hb = r - p;
+      e->hbL = hb;
+    }
     if (project_common(e, c)) return bail(1);
     e->n_points = (double)e->n * (double)e->T;
     e->sum_half = (double)e->n * (double)(e->T / 2);             // sum_i floor(n_i / 2), UpdateSigma.h:49
@@ -536,7 +545,8 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
     } else {
       for (int p = 0; p < e->Pc; p++) {           // (L' c)[p] = sum_r L[r][p] c[r]
         double s = 0;
-        for (int r = (e->Pc == P ? p : 0); r < P; r++) s += e->L[(size_t)p * P + r] * cvec[r];
+        const int r_hi = (e->Pc == P) ? std::min(P - 1, p + e->hbL) : P - 1;
+        for (int r = (e->Pc == P ? p : 0); r <= r_hi; r++) s += e->L[(size_t)p * P + r] * cvec[r];
         h[(size_t)p * QS + f] = s;
       }
     }
@@ -717,7 +727,8 @@ static void unwhiten(const bfmmm_engine* e, const double* CtW, double* BtYW) {
       if (e->identity || e->ragged) { BtYW[(size_t)f * P + r] = CtW[(size_t)f * P + r]; continue; }
       double s = 0;
       const int kmax = (Pc == P) ? r + 1 : Pc;
-      for (int k = 0; k < kmax; k++) s += e->L[(size_t)k * P + r] * CtW[(size_t)f * Pc + k];
+      const int kmin = (Pc == P) ? std::max(0, r - e->hbL) : 0;
+      for (int k = kmin; k < kmax; k++) s += e->L[(size_t)k * P + r] * CtW[(size_t)f * Pc + k];
       BtYW[(size_t)f * P + r] = s;
     }
 }

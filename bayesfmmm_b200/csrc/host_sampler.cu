@@ -12,6 +12,7 @@
 #include <deque>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bfmmm_io.h"
@@ -208,6 +209,10 @@ struct bfmmm_sampler {
   std::vector<double> zpre;     // normals of the Phi / nu block draws generated while the device was busy
   size_t zpre_pos = 0;          // (same streams, same order: the chain is unchanged)
   bool zpre_on = false;
+  std::vector<std::vector<double>> pre_U;   // factors of the blocks' precisions computed in parallel ahead of the draws
+  std::vector<char> pre_ok;
+  std::vector<std::vector<double>> pre_Prec;  // per-thread scratch of prefactor_blocks
+  int pre_next = -1;                        // next prefactored block (-1: none)
   int hbG = 0, hbP = 0;     // half bandwidths of the basis Gram and of the penalty matrix (block draws)
   const double* Hb = nullptr;   // ragged grids: pair cross-Gram band (set before the block draws)
   vecd Hb_own;
@@ -280,6 +285,43 @@ void set_coef(bfmmm_sampler* s, int k, int mm, int dd, const double* in) {
 //   Prec = beta * S_aa * G / sigma^2 + Prior,   rhs = beta * (g_a - G * sum_{b != a} S_ab c_b) / sigma^2
 //   C = pinv(Prec) symmetrised (nu, eta: UpdateNu.h:67-68) or inv(Prec) (Phi, xi: UpdatePhi.h:79)
 //   draw = C rhs + chol_lower(C) z                                (arma::mvnrnd, UpdateNu.h:69)
+// The precision matrices of the blocks of one update (all Phi blocks, or all nu blocks) depend on the
+// statistics and the priors only -- not on the coefficients being drawn -- so for large P (the tensor-product
+// basis of the high-dimensional model, P = 400) they are built and factorised on several host threads
+// before the sequential draws, which then only need the right-hand side and two triangular solves.
+struct PreBlock { int a; const double* prior_full; std::vector<double> prior_diag; };
+constexpr int PREFACTOR_MIN_P = 96;
+void prefactor_blocks(bfmmm_sampler* s, const std::vector<PreBlock>& blocks, const double* WtW, double beta) {
+  const int P = s->P, q = s->q, n = (int)blocks.size();
+  s->pre_U.resize(n); s->pre_ok.assign(n, 0);
+  const double sc = beta / s->sigma_sq;
+  const int hg = s->identity ? 0 : s->hbG;
+  int nt = (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(std::min(n, 8), nt > 1 ? nt / 2 : 1));
+  if ((int)s->pre_Prec.size() < nt) s->pre_Prec.resize(nt);
+  auto work = [&](int t0, int stride) {
+    std::vector<double>& Prec = s->pre_Prec[t0];     // only the band is written and read
+    if (Prec.size() < (size_t)P * P) Prec.resize((size_t)P * P);
+    for (int t = t0; t < n; t += stride) {
+      const PreBlock& b = blocks[t];
+      const double saa = WtW[(size_t)b.a * q + b.a];
+      const int hbb = std::max(hg, b.prior_full ? s->hbP : 0);
+      for (int c = 0; c < P; c++)
+        for (int r = std::max(0, c - hbb); r <= std::min(P - 1, c + hbb); r++) {
+          double g = s->identity ? (r == c ? 1.0 : 0.0) : s->G[(size_t)c * P + r];
+          double pr = b.prior_full ? b.prior_full[(size_t)c * P + r] : (r == c ? b.prior_diag[r] : 0.0);
+          Prec[(size_t)c * P + r] = sc * saa * g + pr;
+        }
+      if (s->pre_U[t].size() < (size_t)P * P) s->pre_U[t].resize((size_t)P * P);
+      s->pre_ok[t] = chol_upper_rev(P, Prec.data(), s->pre_U[t].data(), hbb) ? 1 : 0;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(work, t, nt);
+  work(0, nt);
+  for (auto& x : th) x.join();
+}
+
 int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const double* BtYW, double beta,
                const double* prior_full, const double* prior_diag) {
   const int P = s->P, q = s->q;
@@ -339,6 +381,8 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
     s->rhs[r] = sc * (BtYW[(size_t)a * P + r] - gv);
   }
   const int hbb = std::max(hg, prior_full ? s->hbP : 0);
+  const bool have_factor = s->pre_next >= 0 && s->pre_next < (int)s->pre_U.size() && s->pre_ok[s->pre_next];
+  if (!have_factor)
   for (int c = 0; c < P; c++)
     for (int r = std::max(0, c - hbb); r <= std::min(P - 1, c + hbb); r++) {
       double g = s->identity ? (r == c ? 1.0 : 0.0) : s->G[(size_t)c * P + r];
@@ -351,7 +395,11 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
   if (s->zpre_on) { for (int p = 0; p < P; p++) s->v2[p] = s->zpre[s->zpre_pos++]; }
   else for (int p = 0; p < P; p++) s->v2[p] = s->rng.normal();
   double* U = s->work.data();
-  if (chol_upper_rev(P, s->Prec.data(), U, hb)) {
+  const bool pre = !s->ragged && s->pre_next >= 0 && s->pre_next < (int)s->pre_U.size();
+  const bool pre_good = pre && s->pre_ok[s->pre_next];
+  if (pre_good) U = s->pre_U[s->pre_next].data();
+  if (pre) s->pre_next++;
+  if (pre_good || chol_upper_rev(P, s->Prec.data(), U, hb)) {
     draw_from_rev_chol(P, U, s->rhs.data(), s->v2.data(), s->v1.data(), s->work.data() + (size_t)P * P, hb);
   } else {
     // the dense fallback reads the whole matrix: fill what the band-limited build skipped
@@ -824,31 +872,67 @@ int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtY
   const int K = s->K, P = s->P, M = s->M;
   if (!s->zpre_on) s->rng.open(HP_PHI);
   vecd diag(P);
-  for (int j = 0; j < K; j++) {
+  if (!s->ragged && P >= PREFACTOR_MIN_P) {
+    std::vector<PreBlock> blocks;
+    for (int j = 0; j < K; j++) {
+      double tt = 1;
+      for (int m = 0; m < M; m++) {
+        tt = (m == 0) ? s->delta_(j, 0) : tt * s->delta_(j, m);
+        PreBlock b{s->feat(j, m + 1, 0), nullptr, vecd(P)};
+        for (int p = 0; p < P; p++) b.prior_diag[p] = tt * s->gamma_(j, p, m);
+        blocks.push_back(std::move(b));
+      }
+    }
+    prefactor_blocks(s, blocks, WtW, beta);
+    s->pre_next = 0;
+  }
+  int rc = 0;
+  for (int j = 0; j < K && !rc; j++) {
     double tt = 1;
-    for (int m = 0; m < M; m++) {
+    for (int m = 0; m < M && !rc; m++) {
       tt = (m == 0) ? s->delta_(j, 0) : tt * s->delta_(j, m);      // tilde_tau cumprod, BFMMM.h:1254-1259
       for (int p = 0; p < P; p++) diag[p] = tt * s->gamma_(j, p, m);
-      if (block_draw(s, j, m + 1, 0, WtW, BtYW, beta, nullptr, diag.data())) return 1;
+      rc = block_draw(s, j, m + 1, 0, WtW, BtYW, beta, nullptr, diag.data());
     }
   }
-  return 0;
+  s->pre_next = -1;
+  return rc;
 }
 // updateNu (UpdateNu.h:24-74): blocks j, prior tau_j * P (MV: (1/tau_j) I, :195-196)
 int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   const int K = s->K, P = s->P;
   if (!s->zpre_on) s->rng.open(HP_NU);
   vecd prior((size_t)P * P), diag(P);
-  for (int j = 0; j < K; j++) {
+  std::vector<vecd> priors;
+  if (!s->ragged && P >= PREFACTOR_MIN_P) {
+    std::vector<PreBlock> blocks;
+    if (!s->identity) priors.resize(K);
+    for (int j = 0; j < K; j++) {
+      if (s->identity) {
+        PreBlock b{s->feat(j, 0, 0), nullptr, vecd(P)};
+        for (int p = 0; p < P; p++) b.prior_diag[p] = 1 / s->tau[j];
+        blocks.push_back(std::move(b));
+      } else {
+        priors[j].resize((size_t)P * P);
+        for (size_t e = 0; e < priors[j].size(); e++) priors[j][e] = s->tau[j] * s->Pmat[e];
+        blocks.push_back(PreBlock{s->feat(j, 0, 0), priors[j].data(), vecd()});
+      }
+    }
+    prefactor_blocks(s, blocks, WtW, beta);
+    s->pre_next = 0;
+  }
+  int rc = 0;
+  for (int j = 0; j < K && !rc; j++) {
     if (s->identity) {
       for (int p = 0; p < P; p++) diag[p] = 1 / s->tau[j];
-      if (block_draw(s, j, 0, 0, WtW, BtYW, beta, nullptr, diag.data())) return 1;
+      rc = block_draw(s, j, 0, 0, WtW, BtYW, beta, nullptr, diag.data());
     } else {
       for (size_t e = 0; e < prior.size(); e++) prior[e] = s->tau[j] * s->Pmat[e];
-      if (block_draw(s, j, 0, 0, WtW, BtYW, beta, prior.data(), nullptr)) return 1;
+      rc = block_draw(s, j, 0, 0, WtW, BtYW, beta, prior.data(), nullptr);
     }
   }
-  return 0;
+  s->pre_next = -1;
+  return rc;
 }
 // updateEta (UpdateEta.h:28-94): d outer, j inner; prior tau_eta(j,d) * P (MV: (1/tau_eta) I)
 int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {

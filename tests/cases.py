@@ -14,6 +14,9 @@ CASES = {
     "F_cov": ("common", dict(seed=15, n=29, T=40, K=3, P=8, M=2, D=2)),
     "F_cov_ragged": ("ragged", dict(seed=16, n=23, K=2, P=8, M=2, D=2)),
     "MV_cov": ("mv", dict(seed=17, n=33, R=9, K=3, M=2, D=2)),
+    # P >= 96: the host block draws factorise the (banded) precisions on several threads before drawing
+    "F_common_P100": ("common", dict(seed=18, n=40, T=130, K=2, P=100, M=2)),
+    "MV_R100": ("mv", dict(seed=19, n=40, R=100, K=2, M=2)),
 }
 
 

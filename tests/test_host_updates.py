@@ -131,7 +131,7 @@ def _features(s, d):
     return np.stack(cols, axis=1)
 
 
-@pytest.mark.parametrize("name", ["F_common", "F_common_K2M2", "MV", "F_cov", "MV_cov"])
+@pytest.mark.parametrize("name", ["F_common", "F_common_K2M2", "MV", "F_cov", "MV_cov", "F_common_P100", "MV_R100"])
 @pytest.mark.parametrize("beta", [1.0, 0.6])
 def test_block_draws_from_sufficient_statistics(name, beta):
     """nu / Phi / eta / xi drawn on the host from (W'W, B'Y'W) equal the oracle's per-point loops
