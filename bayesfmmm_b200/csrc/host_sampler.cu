@@ -377,7 +377,7 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
   for (int r = 0; r < P; r++) {
     double gv = 0;
     if (s->identity) gv = s->v1[r];
-    else for (int c = std::max(0, r - hg); c <= std::min(P - 1, r + hg); c++) gv += s->G[(size_t)c * P + r] * s->v1[c];
+    else for (int c = std::max(0, r - hg); c <= std::min(P - 1, r + hg); c++) gv += s->G[(size_t)r * P + c] * s->v1[c];   // G symmetric: contiguous row
     s->rhs[r] = sc * (BtYW[(size_t)a * P + r] - gv);
   }
   const int hbb = std::max(hg, prior_full ? s->hbP : 0);
