@@ -273,7 +273,8 @@ __device__ __forceinline__ double lgamma_near_a(double tot, const PassArgs& a) {
 }
 
 #ifndef BF_Z_MINB
-#define BF_Z_MINB 8       // resident blocks per SM the register allocation of the V = 1 common-grid Z kernel targets
+#define BF_Z_MINB 5       // resident blocks per SM the register allocation of the V = 1 common-grid Z kernel targets
+                          // (96 registers; measured 8: 122 us, 7: 119, 6: 116, 5: 109, 4: 114 -- spills cost more than warps)
 #endif
 template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z_kernel(const PassArgs a) {

@@ -1,3 +1,3 @@
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 900 python tools/configs_bench.py c5 2>&1 | tail -1 | cut -c1-300
-python tools/kbench.py default
+python bench.py --steps 200 --warmup 10 > gpurun_out/bench_new.log 2>&1; tail -1 gpurun_out/bench_new.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], {k: round(v['ms']*1e3,1) for k,v in d['roofline']['kernels'].items()}, d['roofline']['frac'], d['host_split_ms_per_step'])"
