@@ -6,7 +6,7 @@
 namespace bf {
 // functions per thread (V): see pass_kernels.cuh.  BF_TUNE_V builds both variants and lets the
 // environment variable BFMMM_V_CHI pick one at run time (tuning experiments only).
-constexpr int KV = 2;   // measured on B200 (tools/kbench.py): chi 84 us with V = 2 vs 97 us with V = 1
+constexpr int KV = 2;   // measured on B200 (tools/kbench.py): chi 66 us with V = 2 vs 72 us with V = 1
 #ifdef BF_TUNE_V
 static int tune_v() { static int v = -1; if (v < 0) { const char* e = std::getenv("BFMMM_V_CHI"); v = e ? std::atoi(e) : KV; } return v; }
 #define BF_CASE_chi(KK, MM)                                                          \

@@ -88,8 +88,6 @@ struct Philox {
 #define BF_NOINLINE
 #endif
 __host__ __device__ BF_NOINLINE inline double nl_log(double x) { return log(x); }
-__host__ __device__ BF_NOINLINE inline double nl_lgamma(double x) { return lgamma(x); }
-__host__ __device__ BF_NOINLINE inline double nl_pow(double x, double y) { return pow(x, y); }
 
 // log(1 + t) for small |t| by its Taylor series (|t| <= 0.05: truncation < 5e-16), else the library log
 __host__ __device__ inline double log1p_small(double t) {
@@ -191,32 +189,6 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
   return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 __device__ __forceinline__ double u32(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
-// two independent standard normals from three words (53-bit radius uniform, 32-bit angle)
-__device__ __forceinline__ void box_muller_pair(uint32_t w0, uint32_t w1, uint32_t w2, double& n0, double& n1) {
-  const double r = sqrt(-2.0 * log(u53(w0, w1)));
-  double sn, cs;
-  sincospi(2.0 * u32(w2), &sn, &cs);
-  n0 = r * cs; n1 = r * sn;
-}
-// One Marsaglia-Tsang candidate for shape >= 1 from a given normal and accept-uniform; returns false
-// only if the candidate is truly rejected (probability ~1e-3 at shape 10, ~1e-5 at shape 3000; the
-// caller then falls back to RngStream::gamma).  The logarithm of the accept-uniform is evaluated only
-// by the lanes the log-free bound U - 1 < R does not already accept.
-// log_shape = log(shape) is supplied by the caller; lg receives log of the variate.
-__device__ __forceinline__ bool gamma_candidate(double shape, double log_shape, double x, double uu, double& g, double& lg) {
-  const double d = shape - 1.0 / 3.0;
-  const double c = rsqrt(9.0 * d);
-  const double t = c * x;
-  const double v1 = 1.0 + t;
-  const double v = v1 * v1 * v1;
-  const double l3 = 3.0 * log1p_small(t > -0.99 ? t : -0.99);
-  const double R = 0.5 * x * x + d * (1.0 - v + l3);
-  g = d * v;
-  lg = log_shape + log1p_small(-1.0 / (3.0 * shape)) + l3;
-  bool ok = (uu - 1.0 < R);
-  if (!ok) ok = nl_log(uu) < R;
-  return ok && (t > -0.99);
-}
 #endif
 enum { RNG_Z_PROPOSAL = 1, RNG_Z_ACCEPT = 2, RNG_CHI = 3, RNG_Z_PROPOSAL_SLOW = 4 };
 

@@ -109,25 +109,7 @@ __device__ __forceinline__ double band_term_sq(const double (&g)[BWMAX], double 
   for (int j = 1; j < BWMAX; j++) t = fma(2.0 * g[j], wx.prev[j - 1], t);
   return t * x;
 }
-constexpr int ROW_CH = 4;       // rows in flight ahead (common basis)
 constexpr int ROW_CH_RAGGED = 2; // ragged grids: every row also brings bw band rows
-
-// log Gamma(x) for x > 0 when lx = log(x) is already known.  For x >= 16 Stirling's series
-//   (x - 1/2) log x - x + log(2 pi)/2 + 1/(12x) - 1/(360x^3) + 1/(1260x^5) - 1/(1680x^7) + 1/(1188x^9)
-// is exact to double rounding (next term 691/(360360 x^11) < 1e-16 at x = 16) and needs no further
-// transcendental; smaller arguments fall back to the library lgamma.  The Z step evaluates
-// 2(K+1) log-Gammas per function (calc_lB, Distributions.h:51-61).
-__device__ __forceinline__ double lgamma_known_log(double x, double lx) {
-  if (x >= 16.0) {
-    const double r = 1.0 / x, r2 = r * r;
-    double s = fma(r2, 8.417508417508417508e-4, -5.952380952380952381e-4);   //  1/1188, -1/1680
-    s = fma(r2, s, 7.936507936507936508e-4);                                  //  1/1260
-    s = fma(r2, s, -2.777777777777777778e-3);                                 // -1/360
-    s = fma(r2, s, 8.333333333333333333e-2);                                  //  1/12
-    return fma(x - 0.5, lx, -x) + fma(r, s, 0.918938533204672741780329736406);
-  }
-  return nl_lgamma(x);
-}
 
 // Effective coefficients of one function at basis column p:
 //   a[k][0]   = (nu_k + eta_k x_i)[p],   a[k][m+1] = (phi_km + xi_km x_i)[p]     (whitened)
@@ -503,7 +485,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
 // is the already-updated value exactly as in UpdateChi.h:48.
 template <int K, int M, bool COV, int V, bool RG>
 #ifndef BF_CHI_MINB
-#define BF_CHI_MINB 4      // resident blocks per SM targeted by the V = 2 chi kernel (5 and 6 measured slower: spills)
+#define BF_CHI_MINB 4      // resident blocks per SM targeted by the V = 2 chi kernel (3: 68 us, 4: 66 us, 5: 83 us, 6: 134 us -- spills)
 #endif
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : (RG ? 4 : BF_CHI_MINB)) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];

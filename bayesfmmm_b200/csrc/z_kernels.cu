@@ -6,7 +6,7 @@
 namespace bf {
 // functions per thread (V): see pass_kernels.cuh.  BF_TUNE_V builds both variants and lets the
 // environment variable BFMMM_V_Z pick one at run time (tuning experiments only).
-constexpr int KV = 1;   // measured on B200 (tools/kbench.py): Z 202 us with V = 1 vs 241 us with V = 2
+constexpr int KV = 1;   // measured on B200 (tools/kbench.py): Z 122 us with V = 1 vs 138 us with V = 2 (64-register builds)
 #ifdef BF_TUNE_V
 static int tune_v() { static int v = -1; if (v < 0) { const char* e = std::getenv("BFMMM_V_Z"); v = e ? std::atoi(e) : KV; } return v; }
 #define BF_CASE_z(KK, MM)                                                          \

@@ -1,5 +1,5 @@
-for N in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 100 --warmup 10 --no-cpu-baseline 2> gpurun_out/scale_err_$N.log | tail -1 > gpurun_out/scale_$N.json
-python -c "
-import sys,json; d=json.loads(open('gpurun_out/scale_$N.json').read()); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'])"
-done
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+export BFMMM_LIB=$PWD/tools/lib_small.so
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
+ncu --set full --clock-control none -k regex:'z_kernel|chi_kernel|ssr_kernel|stats_kernel' -s 20 -c 4 -o gpurun_out/prof_r1_final python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_f2.log 2>&1
+tail -1 gpurun_out/ncu_f2.log | cut -c1-80
