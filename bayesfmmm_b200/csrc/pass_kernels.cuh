@@ -487,7 +487,10 @@ template <int K, int M, bool COV, int V, bool RG>
 #ifndef BF_CHI_MINB
 #define BF_CHI_MINB 4      // resident blocks per SM targeted by the V = 2 chi kernel (3: 68 us, 4: 66 us, 5: 83 us, 6: 134 us -- spills)
 #endif
-__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? 8 : (RG ? 4 : BF_CHI_MINB)) chi_kernel(const PassArgs a) {
+#ifndef BF_CHI1_MINB
+#define BF_CHI1_MINB 8
+#endif
+__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (RG ? 4 : BF_CHI_MINB)) chi_kernel(const PassArgs a) {
   extern __shared__ double g[];
   build_log_table();
   stage_globals(a, g);

@@ -230,7 +230,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 __host__ __device__ inline int tm_align128(int bytes) { return (bytes + 127) & ~127; }
 
 template <int MT, int NT>
-__global__ void __launch_bounds__(TM_THREADS, 2) stats_kernel_tma(const StatsArgs a, const __grid_constant__ StatsTmaMaps tm) {
+#ifndef BF_ST_BPS
+#define BF_ST_BPS 2      // resident blocks per SM of the statistics kernels (grid = BF_ST_BPS * SM count)
+#endif
+__global__ void __launch_bounds__(TM_THREADS, BF_ST_BPS) stats_kernel_tma(const StatsArgs a, const __grid_constant__ StatsTmaMaps tm) {
   constexpr int TILES = MT * NT + NT * NT;
   extern __shared__ __align__(128) unsigned char tm_smem[];
   __shared__ double s_acc[TILES * 64];
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(256) stats_final_kernel(const StatsArgs a, int
   if (lane == 0) { if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t; }
 }
 
-int stats_blocks(int sm_count) { return 2 * sm_count; }
+int stats_blocks(int sm_count) { return BF_ST_BPS * sm_count; }
 
 static inline void stats_shape(int P, int q, int& MT, int& NT, int& gy) {
   NT = (q + 7) / 8;
@@ -431,7 +434,7 @@ static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& us
   const size_t stage = (size_t)tm_align128(MT * 8 * TM_STRIDE) + tm_align128(a.K * TM_STRIDE) + tm_align128(a.M * TM_STRIDE) +
                        tm_align128(a.D * TM_STRIDE);
   const size_t smem = (size_t)TM_STAGES * stage;
-  if (smem > 100 * 1024) return 0;                            // two blocks per SM
+  if (smem > (BF_ST_BPS == 2 ? 100 : 64) * 1024) return 0;    // BF_ST_BPS blocks per SM
   int dev = 0;
   cudaGetDevice(&dev);
   static std::set<std::pair<int, size_t>> configured;       // per device: the attribute is per context
