@@ -199,7 +199,10 @@ constexpr int TM_THREADS = (TM_CONSUMERS + 1) * 32;
 constexpr int TM_FN = 64;                       // functions consumed per stage (8 per consumer warp)
 constexpr int TM_BOX = 72;                      // functions copied per stage row
 constexpr int TM_STRIDE = TM_BOX * 8;           // shared-memory row pitch in bytes (576)
-constexpr int TM_STAGES = 4;
+#ifndef BF_TM_STAGES
+#define BF_TM_STAGES 4
+#endif
+constexpr int TM_STAGES = BF_TM_STAGES;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
