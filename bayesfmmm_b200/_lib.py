@@ -23,7 +23,7 @@ class Config(C.Structure):
 # every symbol include/bfmmm.h and include/bfmmm_debug.h declare
 EXPORTS = [
     "bfmmm_create", "bfmmm_destroy", "bfmmm_last_error", "bfmmm_launch_count", "bfmmm_get_basis",
-    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_get_state_rows", "bfmmm_sigma_draw_async", "bfmmm_sigma_wait", "bfmmm_get_state_begin", "bfmmm_get_state_wait", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
+    "bfmmm_set_state", "bfmmm_get_state", "bfmmm_get_state_rows", "bfmmm_marginal_loglik", "bfmmm_cpo_reset", "bfmmm_cpo_accumulate", "bfmmm_cpo_get", "bfmmm_sigma_draw_async", "bfmmm_sigma_wait", "bfmmm_get_state_begin", "bfmmm_get_state_wait", "bfmmm_set_globals", "bfmmm_update_z", "bfmmm_update_chi",
     "bfmmm_ssr", "bfmmm_suffstats", "bfmmm_get_gram", "bfmmm_seed", "bfmmm_stats_buffer_dev",
     "bfmmm_update_z_async", "bfmmm_update_chi_async", "bfmmm_ssr_async", "bfmmm_suffstats_async",
     "bfmmm_read_stats", "bfmmm_clear_ssr_after", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts", "bfmmm_suffstats_ragged",

@@ -44,6 +44,13 @@ struct PassArgs {
   const double* __restrict__ eps;   // chi: [M][ld] or nullptr
   double* __restrict__ acc_out;     // optional per-function acceptance log-ratio (diagnostics)
   double* __restrict__ draws_out;   // optional: device-RNG draws written back ([K+1][ld] / [M][ld])
+  // marginal log-likelihood / CPO accumulation (chi_kernel<..., CPO = true>)
+  const double* __restrict__ ni;    // points per function (ragged grids) or nullptr: npts_common
+  double npts_common;
+  double* __restrict__ logl_out;    // optional per-function marginal log-likelihood
+  double* __restrict__ cpo_m;       // running max and scaled sum of exp(-logl) per function (or nullptr)
+  double* __restrict__ cpo_s;
+  int cpo_first;
   // RNG
   uint64_t key, iteration, global_offset;
   // reduction
@@ -257,6 +264,7 @@ int launch_ssr_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_mloglik(const PassArgs& a, int K, int M, bool ragged, cudaStream_t s);
 int pass_grid(int ld, int v);
 
 // TMA descriptors of the statistics kernel's operands (see stats_kernels.cu)

@@ -47,6 +47,9 @@ struct bfmmm_engine {
   int bw = 0, npairs = 0;
   bool ragged = false;
   double *snapZ = nullptr, *snapLZ = nullptr, *snapChi = nullptr;   // device copy of (Z, log Z, chi) for tempered transitions
+  double *ni = nullptr;                          // ragged grids: points per function (marginal log-likelihood)
+  double *cpo_m = nullptr, *cpo_s = nullptr, *logl = nullptr;   // CPO accumulators, per-function marginal log-likelihood
+  int64_t cpo_count = 0;
   double *rbZ = nullptr, *rbChi = nullptr;       // device staging of an overlapped read-back (bfmmm_get_state_begin)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
@@ -109,6 +112,7 @@ void free_all(bfmmm_engine* e) {
   if (e->ev_snap) cudaEventDestroy(e->ev_snap);
   if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   cudaFree(e->rbZ); cudaFree(e->rbChi);
+  cudaFree(e->ni); cudaFree(e->cpo_m); cudaFree(e->cpo_s); cudaFree(e->logl);
   for (int i = 0; i < N_STAGE; i++) {
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
@@ -264,6 +268,12 @@ int project_ragged(bfmmm_engine* e, const bfmmm_config* c) {
     sum_half += (double)(ni / 2);                              // integer division, UpdateSigma.h:49
   }
   e->n_points = (double)N; e->sum_half = sum_half;
+  {
+    std::vector<double> nih((size_t)e->ld, 0.0);
+    for (int i = 0; i < n; i++) nih[i] = (double)(c->off[i + 1] - c->off[i]);
+    CU(cudaMalloc(&e->ni, (size_t)e->ld * 8));
+    CU(cudaMemcpy(e->ni, nih.data(), (size_t)e->ld * 8, cudaMemcpyHostToDevice));
+  }
   std::vector<int64_t> off(c->off, c->off + n + 1);
   for (auto& o : off) o -= c->off[0];
   int64_t* d_off = nullptr; double *d_y = nullptr, *d_t = nullptr, *d_B = nullptr, *d_kn = nullptr; int* d_bw = nullptr;
@@ -666,6 +676,60 @@ int bfmmm_ssr(bfmmm_engine* e, double* ssr, double* sum_half, double* n_points) 
   if (ssr) *ssr = e->h_stats[0];
   if (sum_half) *sum_half = e->sum_half;
   if (n_points) *n_points = e->n_points;
+  return 0;
+}
+
+// ---- post-processing: per-function marginal log-likelihood and CPO (calcLikelihoodCPO, CalculateLikelihood.h:344-385)
+static int mloglik_launch(bfmmm_engine* e, bool accumulate) {
+  if (!e->logl) CU(cudaMalloc(&e->logl, (size_t)e->ld * 8));
+  if (accumulate && !e->cpo_m) {
+    CU(cudaMalloc(&e->cpo_m, (size_t)e->ld * 8));
+    CU(cudaMalloc(&e->cpo_s, (size_t)e->ld * 8));
+  }
+  bf::PassArgs a;
+  fill_pass(e, a, 1.0);
+  a.ni = e->ni; a.npts_common = e->identity ? (double)e->P : (double)e->T;
+  a.logl_out = e->logl;
+  if (accumulate) { a.cpo_m = e->cpo_m; a.cpo_s = e->cpo_s; a.cpo_first = e->cpo_count == 0 ? 1 : 0; }
+  int rc = bf::launch_mloglik(a, e->K, e->M, e->ragged, e->stream);
+  if (rc) return fail("marginal log-likelihood kernel launch failed rc=" + std::to_string(rc));
+  if (accumulate) e->cpo_count++;
+  return 0;
+}
+// log p(y_i | Z_i, globals, sigma^2) with chi_i integrated out, for the current state and the globals last pushed
+int bfmmm_marginal_loglik(bfmmm_engine* e, double* logl /* n */) {
+  if (!e || !logl) return fail("null argument");
+  CU(cudaSetDevice(e->device));
+  if (mloglik_launch(e, false)) return 1;
+  CU(cudaMemcpyAsync(logl, e->logl, (size_t)e->n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int bfmmm_cpo_reset(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  e->cpo_count = 0;
+  return 0;
+}
+// adds the current state (one retained iteration) to the running harmonic mean; asynchronous
+int bfmmm_cpo_accumulate(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  return mloglik_launch(e, true);
+}
+// CPO_i = log L - log sum_l exp(-logl_il) over the L accumulated iterations (log scale unless log_scale == 0)
+int bfmmm_cpo_get(bfmmm_engine* e, double* cpo /* n */, int log_scale) {
+  if (!e || !cpo) return fail("null argument");
+  if (e->cpo_count == 0) return fail("bfmmm_cpo_get: nothing accumulated");
+  CU(cudaSetDevice(e->device));
+  std::vector<double> m((size_t)e->n), sv((size_t)e->n);
+  CU(cudaMemcpyAsync(m.data(), e->cpo_m, (size_t)e->n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(sv.data(), e->cpo_s, (size_t)e->n * 8, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  const double lL = std::log((double)e->cpo_count);
+  for (int i = 0; i < e->n; i++) {
+    const double v = lL - (m[i] + std::log(sv[i]));
+    cpo[i] = log_scale ? v : std::exp(v);
+  }
   return 0;
 }
 

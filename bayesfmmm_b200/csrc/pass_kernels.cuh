@@ -483,7 +483,14 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
 // Gram G[m][n] = ph_m . ph_n and r[m] = ph_m . (y - B mu) are accumulated once (in coefficient
 // space), then the reference's sequential m = 0..M-1 sweep is run on them, so chi(i,n) for n < m
 // is the already-updated value exactly as in UpdateChi.h:48.
-template <int K, int M, bool COV, int V, bool RG>
+// CPO = true turns the same accumulation into the per-function MARGINAL log-likelihood (chi integrated
+// out) that the reference's calcLikelihoodCPO evaluates per stored iteration (CalculateLikelihood.h:344-385):
+// with U = B [u_1 .. u_M], cov = U U' + sigma^2 I and G = U'U (M x M, accumulated below), r = U'(y - B mu),
+//   log det cov = (n_i - M) log sigma^2 + log det(sigma^2 I_M + G)
+//   (y - B mu)' cov^{-1} (y - B mu) = (|y - B mu|^2 - r'(sigma^2 I_M + G)^{-1} r) / sigma^2
+// (matrix determinant lemma / Woodbury), so the n_i x n_i covariance the reference factorises never exists.
+// The CPO's harmonic mean over iterations is kept as a running log-sum-exp of -logl per function.
+template <int K, int M, bool COV, int V, bool RG, bool CPO = false>
 #ifndef BF_CHI_MINB
 #define BF_CHI_MINB 4      // resident blocks per SM targeted by the V = 2 chi kernel (3: 68 us, 4: 66 us, 5: 83 us, 6: 134 us -- spills)
 #endif
@@ -503,7 +510,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
     if constexpr (!RG) rows.begin(a.Ct + i0, a.ld);
     // the normals do not depend on the state: generated first, while the loads above are in flight
     double eps[V][M];
-    if (!a.eps) {
+    if (!CPO && !a.eps) {
 #pragma unroll
       for (int v = 0; v < V; v++) {
         // (M+1)/2 Box-Muller pairs, one Philox block each (three words used)
@@ -584,6 +591,54 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
       const double nogb[1][V] = {};
       rows.run(a.P4, [&](int p, const double (&c)[V]) { body(p, c, nogb); });
     }
+    if constexpr (CPO) {
+      double rssv[V];
+      ldv<V>(a.rss + i0, rssv);
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        // Cholesky of A = sigma^2 I + G in registers, w = L^{-1} r
+        double L[M][M], w[M], logdet = 0, quad = 0;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          double dj = G[v][j][j] + a.sigma_sq;
+#pragma unroll
+          for (int k = 0; k < j; k++) dj = fma(-L[j][k], L[j][k], dj);
+          const double lj = sqrt(dj);
+          L[j][j] = lj;
+          logdet += nl_log(dj);                       // = 2 log L_jj
+          double wj = r[v][j];
+#pragma unroll
+          for (int k = 0; k < j; k++) wj = fma(-L[j][k], w[k], wj);
+          w[j] = wj / lj;
+          quad = fma(w[j], w[j], quad);
+#pragma unroll
+          for (int i = j + 1; i < M; i++) {
+            double t = G[v][j][i];                      // upper triangle holds G[j][i], j <= i
+#pragma unroll
+            for (int k = 0; k < j; k++) t = fma(-L[i][k], L[j][k], t);
+            L[i][j] = t / lj;
+          }
+        }
+        const double ni = a.ni ? a.ni[i0 + v] : a.npts_common;
+        const double lsig = nl_log(a.sigma_sq);
+        const double resid = rssv[v] + d0[v];
+        const double logl = -0.5 * ni * 1.8378770664093454836 - 0.5 * ((ni - M) * lsig + logdet) - 0.5 * (resid - quad) / a.sigma_sq;
+        if (i0 + v < a.n) {
+          if (a.logl_out) a.logl_out[i0 + v] = logl;
+          if (a.cpo_m) {                                // running log-sum-exp of -logl
+            const double x = -logl;
+            if (a.cpo_first) { a.cpo_m[i0 + v] = x; a.cpo_s[i0 + v] = 1.0; }
+            else {
+              const double mo = a.cpo_m[i0 + v], so = a.cpo_s[i0 + v];
+              const double mn = fmax(mo, x);
+              a.cpo_m[i0 + v] = mn;
+              a.cpo_s[i0 + v] = so * exp(mo - mn) + exp(x - mn);
+            }
+          }
+        }
+      }
+      continue;
+    }
     if (a.eps) {
       double t[V];
 #pragma unroll
@@ -637,7 +692,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
       }
     }
   }
-  grid_reduce<1>(red, a);
+  if constexpr (!CPO) grid_reduce<1>(red, a);
 }
 
 // ================================================================= residual sum of squares

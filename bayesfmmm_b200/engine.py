@@ -124,6 +124,24 @@ class Engine:
         """D2H copy into caller-owned column-major buffers (the reference's chain slices)."""
         self._chk(self._lib.bfmmm_get_state(self._h, _p(Z), _p(chi)))
 
+    # ------------------------------------------------------------------ post-processing (CPO)
+    def marginal_loglik(self):
+        """log p(y_i | Z_i, globals, sigma^2), chi_i integrated out (the summand of calcLikelihoodCPO)."""
+        out = np.zeros(self.n)
+        self._chk(self._lib.bfmmm_marginal_loglik(self._h, _p(out)))
+        return out
+
+    def cpo_reset(self):
+        self._chk(self._lib.bfmmm_cpo_reset(self._h))
+
+    def cpo_accumulate(self):
+        self._chk(self._lib.bfmmm_cpo_accumulate(self._h))
+
+    def cpo_get(self, log_scale=True):
+        out = np.zeros(self.n)
+        self._chk(self._lib.bfmmm_cpo_get(self._h, _p(out), C.c_int(1 if log_scale else 0)))
+        return out
+
     def get_state_begin(self, Z=None, chi=None):
         """Starts an overlapped read-back of the current (Z, chi) into caller-owned column-major buffers
         (page-locked for the copy to be asynchronous); later updates run while it is in flight."""

@@ -93,6 +93,17 @@ int bfmmm_sigma_draw_async(bfmmm_engine* e, double a, double scale_ssr, double b
                            uint64_t iteration, uint32_t purpose);
 int bfmmm_sigma_wait(bfmmm_engine* e, double* ssr, double* sigma_sq);
 
+/* ---- post-processing on the device ------------------------------------------------------
+ * calcLikelihoodCPO (CalculateLikelihood.h:344-385, called by ConditionalPredictiveOrdinates,
+ * src/PostProcessing.cpp:6509): per stored iteration the marginal log-likelihood of every function with chi
+ * integrated out, then CPO_i = log L + min_l logl_il - log sum_l exp(min_l logl_il - logl_il).  The caller
+ * replays the stored iterations (bfmmm_set_state + bfmmm_set_globals per retained iteration, burn-in skipped)
+ * and calls bfmmm_cpo_accumulate for each; bfmmm_cpo_get returns the CPO (log scale unless log_scale == 0). */
+int bfmmm_marginal_loglik(bfmmm_engine* e, double* logl /* n */);
+int bfmmm_cpo_reset(bfmmm_engine* e);
+int bfmmm_cpo_accumulate(bfmmm_engine* e);
+int bfmmm_cpo_get(bfmmm_engine* e, double* cpo /* n */, int log_scale);
+
 /* device-side snapshot / restore of (Z, chi): a rejected tempered transition keeps the
  * pre-transition slice (BFMMM.h:1631-1651) */
 int bfmmm_state_snapshot(bfmmm_engine* e);

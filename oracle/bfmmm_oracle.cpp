@@ -605,6 +605,56 @@ extern "C" int orc_loglik(const orc_data* d, const orc_state* s, double* loglik)
   return 0;
 }
 
+// Marginal (chi integrated out) log-likelihood of every function for ONE stored iteration: the summand of
+// calcLikelihoodCPO (CalculateLikelihood.h:360-375):
+//   mean_i = sum_k Z_ik B_i (nu_k + eta_k x_i)
+//   cov_i  = sum_m (B_i u_im)(B_i u_im)' + sigma^2 I,  u_im = sum_k Z_ik (phi_km + xi_km x_i)
+//            (:364-369 sums Z_ik Z_ik1 B (.)(.)' B' over k, k1: the same rank-one terms)
+//   logl_i = -(n_i / 2) log(2 pi) - log det(cov_i) / 2 - (y_i - mean_i)' cov_i^{-1} (y_i - mean_i) / 2
+// evaluated densely (n_i x n_i covariance, Cholesky), as the reference does.  The CPO itself is
+//   CPO_i = log L + min_l logl_il - log sum_l exp(min_l logl_il - logl_il)          (:376-382)
+// over the L retained iterations (the tests restate that line in numpy).
+extern "C" int orc_marginal_loglik(const orc_data* d, const orc_state* s, double* logl_out) {
+  View v(d, s);
+  PointEval pe(v);
+  const int n = v.n, K = v.K, M = v.M;
+  for (int i = 0; i < n; i++) {
+    if (v.D) pe.set_function(i);
+    const int64_t T = v.npts(i);
+    std::vector<double> res((size_t)T), U((size_t)T * std::max(M, 1)), cov((size_t)T * T, 0.0), L;
+    for (int64_t l = 0; l < T; l++) {
+      pe.eval(i, l);
+      double mean = 0;
+      for (int k = 0; k < K; k++) mean += v.Z(i, k) * pe.an[k];
+      res[l] = v.y(i, l) - mean;
+      for (int m = 0; m < M; m++) {
+        double u = 0;
+        for (int k = 0; k < K; k++) u += v.Z(i, k) * pe.fn[(size_t)k * M + m];
+        U[(size_t)m * T + l] = u;
+      }
+    }
+    for (int m = 0; m < M; m++)
+      for (int64_t c = 0; c < T; c++)
+        for (int64_t r = 0; r < T; r++) cov[(size_t)c * T + r] += U[(size_t)m * T + r] * U[(size_t)m * T + c];
+    for (int64_t l = 0; l < T; l++) cov[(size_t)l * T + l] += s->sigma_sq;
+    L.assign((size_t)T * T, 0.0);
+    if (orc_chol_lower((int)T, cov.data(), L.data())) return 1;
+    double logdet = 0;
+    for (int64_t l = 0; l < T; l++) logdet += 2 * std::log(L[(size_t)l * T + l]);
+    // w = L^{-1} res, quadratic form = |w|^2
+    std::vector<double> w(res);
+    double quad = 0;
+    for (int64_t r = 0; r < T; r++) {
+      double t = w[r];
+      for (int64_t c = 0; c < r; c++) t -= L[(size_t)c * T + r] * w[c];
+      w[r] = t / L[(size_t)r * T + r];
+      quad += w[r] * w[r];
+    }
+    logl_out[i] = -(0.5 * (double)T) * std::log(2 * M_PI) - 0.5 * logdet - 0.5 * quad;
+  }
+  return 0;
+}
+
 // ================================================================= Gaussian block updates
 static std::vector<double> scaled(const double* Pmat, int P, double c) {
   std::vector<double> pr((size_t)P * P);

@@ -216,6 +216,22 @@ def loglik(d: Data, s: State):
     return ll.value
 
 
+def marginal_loglik(d: Data, s: State):
+    """Per-function marginal log-likelihood (chi integrated out) of one stored iteration: the summand of
+    calcLikelihoodCPO (CalculateLikelihood.h:360-375)."""
+    out = np.zeros(d.n)
+    dc, sc = d.c(), s.c()
+    _chk(lib().orc_marginal_loglik(C.byref(dc), C.byref(sc), _p(out)), "marginal_loglik")
+    return out
+
+
+def cpo(logl):
+    """CPO_i from the L x n matrix of retained per-iteration marginal log-likelihoods (CalculateLikelihood.h:376-382)."""
+    logl = np.asarray(logl, dtype=float)
+    mn = logl.min(axis=0)
+    return np.log(logl.shape[0]) + mn - np.log(np.exp(mn[None, :] - logl).sum(axis=0))
+
+
 def update_nu(d: Data, s: State, tau, Pmat, z, beta=1.0):
     tau = _f(tau); z = _f(z)
     Pm = _f(Pmat) if Pmat is not None else None

@@ -114,6 +114,17 @@ def loglik(d, s):
     return out.value
 
 
+def cpo(d, states, burnin_prop=0.0):
+    """calcLikelihoodCPO of the reference over the stored iterations `states` (functional models)."""
+    tape([])
+    dc = d.c()
+    scs = [st.c() for st in states]
+    arr = (type(scs[0]) * len(scs))(*scs)
+    out = np.zeros(d.n)
+    _done(lib().ref_cpo(C.byref(dc), arr, len(scs), C.c_double(burnin_prop), out.ctypes.data_as(C.POINTER(C.c_double))), "cpo")
+    return out
+
+
 def update_nu(d, s, tau, Pmat, z, beta=1.0, tempered=False):
     tape(np.asarray(z).ravel(order="F"))             # P x K column-major = block j, then p
     out = np.zeros((d.K, d.P), order="F")

@@ -190,6 +190,30 @@ int ref_loglik(const orc_data* d, const orc_state* s, double* ll) {
   } catch (std::exception& e) { std::cerr << "ref_loglik: " << e.what() << "\n"; return 1; }
 }
 
+// calcLikelihoodCPO (CalculateLikelihood.h:344-385) over `iters` stored iterations (states[l]); with one
+// iteration and burnin 0 the returned CPO_i is logl_i itself.  Without covariates the caller of the
+// reference passes a zero covariate column and zero eta / xi (src/PostProcessing.cpp:6455-6475).
+int ref_cpo(const orc_data* d, const orc_state* states, int iters, double burnin_prop, double* cpo_out) {
+  try {
+    if (d->identity_basis) return 1;
+    const int n = d->n, K = d->K, P = d->P, M = d->M, D = d->D, De = D ? D : 1;
+    Ctx c0(d, &states[0]);
+    arma::cube nu(K, P, iters), Z(n, K, iters), chi(n, M, iters);
+    arma::field<arma::cube> eta(iters, 1), Phi(iters, 1), xi(iters, K);
+    arma::vec sigma(iters);
+    for (int l = 0; l < iters; l++) {
+      Ctx c(d, &states[l]);
+      nu.slice(l) = c.nu; Z.slice(l) = c.Z; chi.slice(l) = c.chi; sigma(l) = c.sigma; Phi(l, 0) = c.Phi;
+      if (D) { eta(l, 0) = c.eta; for (int k = 0; k < K; k++) xi(l, k) = c.xi(0, k); }
+      else { eta(l, 0) = arma::zeros(P, 1, K); for (int k = 0; k < K; k++) xi(l, k) = arma::zeros(P, 1, M); }
+    }
+    arma::mat X = D ? c0.X : arma::mat(arma::zeros(n, De));
+    arma::vec out = BayesFMMM::calcLikelihoodCPO(c0.y_f, c0.B_f, nu, eta, Phi, xi, Z, chi, X, sigma, iters, burnin_prop);
+    for (int i = 0; i < n; i++) cpo_out[i] = out(i);
+    return 0;
+  } catch (std::exception& e) { std::cerr << "ref_cpo: " << e.what() << "\n"; return 1; }
+}
+
 // Draw order: for j: P normals.
 int ref_update_nu(const orc_data* d, const orc_state* s, const double* tau, const double* Pmat,
                   double beta, int tempered, double* nu_out) {

@@ -316,7 +316,9 @@ inline double pnorm(double x, double mu, double sd, int lower, int lg) {
 }  // namespace R
 
 namespace Rcpp {
-static std::ostream& Rcout = std::cout;
+// progress output of the reference is discarded (a stream without a buffer: every insertion is a no-op)
+static std::ostream Rcout_null(nullptr);
+static std::ostream& Rcout = Rcout_null;
 inline void checkUserInterrupt() {}
 }
 

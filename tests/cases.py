@@ -58,3 +58,16 @@ def draws(name, s, a_Z_PM=A_Z_PM):
         gamma_xi=rng.gamma(2.0, 1.0, (K, P, max(D, 1), M)) + 0.1,
         tilde_tau_xi=np.asfortranarray(rng.gamma(2.0, 1.0, (K, M, max(D, 1))) + 0.5),
     )
+
+
+def stored_iterations(name, st, L=5):
+    """A short 'stored chain' for the CPO tests: L states around st (perturbed nu, Phi, Z, sigma^2)."""
+    rng = np.random.default_rng(sum(ord(c) for c in name) + 77)
+    out = []
+    for l in range(L):
+        Z = st.Z * np.exp(0.05 * rng.normal(size=st.Z.shape))
+        Z = np.asfortranarray(Z / Z.sum(axis=1, keepdims=True))
+        out.append(orc.State(nu=np.asfortranarray(st.nu + 0.02 * rng.normal(size=st.nu.shape)),
+                             Phi=np.asfortranarray(st.Phi * (1 + 0.05 * rng.normal(size=st.Phi.shape))),
+                             Z=Z, chi=st.chi, sigma_sq=st.sigma_sq * (1 + 0.2 * rng.uniform()), eta=st.eta, xi=st.xi))
+    return out

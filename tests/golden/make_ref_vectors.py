@@ -37,6 +37,8 @@ def main():
                 out[key + "eta"] = ref.update_eta(d, st, dr["tau_eta"], Pm, dr["z_eta"], beta, t)
                 out[key + "xi"] = ref.update_xi(d, st, dr["gamma_xi"], dr["tilde_tau_xi"], dr["z_xi"], beta, t)
         out[f"{name}|loglik"] = ref.loglik(d, st)
+        if not d.identity_basis and "P100" not in name:      # calcLikelihoodCPO over a short stored chain
+            out[f"{name}|cpo"] = ref.cpo(d, cases.stored_iterations(name, st))
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_updates.npz"), **out)
     print("wrote", len(out), "reference vectors")
 

@@ -227,3 +227,27 @@ def test_device_rng_distributions():
         shape = a_Z * Z[0, k]
         assert sst.kstest(gam[:, k], "gamma", args=(shape,)).pvalue > 1e-3, (k, shape)
     eng.close()
+
+
+@pytest.mark.parametrize("name", GPU_CASES)
+def test_marginal_loglik_and_cpo(name):
+    """Post-processing on the device: the per-function marginal log-likelihood (chi integrated out, through the
+    M x M Woodbury form) and the CPO accumulated over a short stored chain equal the oracle's dense
+    n_i x n_i evaluation of calcLikelihoodCPO (CalculateLikelihood.h:344-385)."""
+    s, d, st, eng = engine_for(name)
+    states = cases.stored_iterations(name, st)
+    eng.cpo_reset()
+    L = []
+    for x in states:
+        eng.set_state(x.Z, x.chi)
+        eng.set_globals(x.nu, x.Phi, x.sigma_sq, eta=x.eta, xi=x.xi)
+        lg = eng.marginal_loglik()
+        if not d.identity_basis:
+            lo = orc.marginal_loglik(d, x)
+            assert np.max(np.abs(lg - lo) / np.abs(lo)) < TOL
+        L.append(lg)
+        eng.cpo_accumulate()
+    cpo = eng.cpo_get()
+    assert np.max(np.abs(cpo - orc.cpo(np.stack(L))) / np.abs(cpo)) < 1e-12
+    assert np.allclose(eng.cpo_get(log_scale=False), np.exp(cpo), rtol=1e-12)
+    eng.close()

@@ -52,3 +52,15 @@ def test_block_updates(name, beta):
                ref.update_eta(d, st, dr["tau_eta"], Pm, dr["z_eta"], beta, temp), 1e-9)
         _close(orc.update_xi(d, st, dr["gamma_xi"], dr["tilde_tau_xi"], dr["z_xi"], beta),
                ref.update_xi(d, st, dr["gamma_xi"], dr["tilde_tau_xi"], dr["z_xi"], beta, temp), 1e-9)
+
+
+@pytest.mark.parametrize("name", [c for c in cases.CASES if cases.CASES[c][0] != "mv" and "P100" not in c])
+def test_cpo_matches_calcLikelihoodCPO(name):
+    """The oracle's per-iteration marginal log-likelihood + the harmonic-mean line equal the reference's
+    calcLikelihoodCPO (CalculateLikelihood.h:344-385), with and without burn-in."""
+    s, d, st = cases.build(name)
+    states = cases.stored_iterations(name, st)
+    L = np.stack([orc.marginal_loglik(d, x) for x in states])
+    _close(L[0], ref.cpo(d, states[:1]), 1e-12)
+    _close(orc.cpo(L), ref.cpo(d, states), 1e-12)
+    _close(orc.cpo(L[2:]), ref.cpo(d, states, 0.5), 1e-12)      # floor(0.5 * 5) = 2 iterations dropped
