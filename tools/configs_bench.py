@@ -102,6 +102,41 @@ def c5(n=200_000):
     run(f"C5 high-dimensional K=4 P=400 (20x20 tensor basis) T=1024 n={n}", eng, smp, bf.SWEEP_FULL, steps=10, warm=2)
 
 
+def cpo(n=1_000_000):
+    """CPO accumulation (calcLikelihoodCPO per retained iteration) at the benchmark shape, next to the reference's
+    own function (oracle/_ref, dense n_i x n_i covariance per function) on a few functions."""
+    s = synth.functional_common(seed=1, n=n, T=200, K=3, P=20, M=3)
+    eng = bf.Engine(model=FUNCTIONAL, n=n, K=3, P=20, M=3, y=s["y"], T=200, t=s["t"], degree=3,
+                    internal_knots=s["internal_knots"], boundary=(0.0, 1000.0))
+    eng.set_state(s["Z"], s["chi"])
+    eng.set_globals(s["par"]["nu"], s["par"]["Phi"], 0.01)
+    eng.cpo_reset()
+    for _ in range(3):
+        eng.cpo_accumulate()
+    eng.sync()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        eng.cpo_accumulate()
+    eng.sync()
+    dt = (time.perf_counter() - t0) / 50
+    out = {"config": f"CPO accumulation, functional K=3 P=20 M=3 n={n} T=200", "ms_per_iteration": dt * 1e3}
+    try:
+        from oracle import oracle as orc, ref
+        if ref.available():
+            m = 20
+            d = orc.Data(n=m, K=3, P=20, M=3, y=s["y"][:m].ravel(), B=np.tile(s["B"], (m, 1)), off=np.arange(m + 1, dtype=np.int64) * 200)
+            st = orc.State(nu=s["par"]["nu"], Phi=s["par"]["Phi"], Z=s["Z"][:m], chi=s["chi"][:m], sigma_sq=0.01)
+            t0 = time.perf_counter()
+            ref.cpo(d, [st])
+            tr = time.perf_counter() - t0
+            out["reference_s_per_iteration_extrapolated"] = tr / m * n
+            out["reference_sample"] = f"{m} functions, {tr:.3f} s, one host core (oracle/_ref over the shim)"
+    except Exception as exc:
+        out["reference_sample"] = f"unavailable: {exc}"
+    print(json.dumps(out), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]
     if "c1" in which:
@@ -114,3 +149,5 @@ if __name__ == "__main__":
         c4()
     if "c5" in which:
         c5()
+    if "cpo" in which:
+        cpo()
