@@ -277,6 +277,11 @@ def run_ours(a):
     prof1 = smp.profile()
     value = world * a.steps / (ms * 1e-3)
 
+    # ---- the Theta_est sweep (BFMMM_Theta, BFMMM.h:1253-1298: Phi, delta, A, gamma, tau, sigma^2, chi, loglik; Z and nu fixed)
+    smp.run(bf.SWEEP_THETA, 3)
+    ms_theta = timed(lambda k: smp.run(bf.SWEEP_THETA, k), a.steps)
+    theta_est = {"value": world * a.steps / (ms_theta * 1e-3), "unit": "Theta_est sweeps/s (Z, nu fixed)", "ms_per_step": ms_theta / a.steps}
+
     # ---- e2e: the same sweep through the host-buffer API, copying the new Z and chi back into the
     # caller's chain storage every iteration (what the reference's chain containers require)
     # page-locked chain slots (two, used alternately: slice i travels while sweep i+1 runs)
@@ -366,6 +371,7 @@ def run_ours(a):
            "host_split_ms_per_step": {k.replace("_s", ""): (prof1[k] - prof0[k]) / a.steps * 1e3 for k in prof1},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "steps": e_steps, "ms_per_step": ms_e / e_steps},
+           "theta_est_sweep": theta_est,
            "ess_z": ess_z,
            "roofline": roofline}
     if rank == 0:
