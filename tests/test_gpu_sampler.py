@@ -274,3 +274,34 @@ def test_device_sigma_draw_is_the_host_draw():
     assert np.max(np.abs(a[0][0] - b[0][0]) / np.abs(b[0][0])) < 1e-12      # first sweep: identical up to rounding
     assert np.max(np.abs(a[0] - b[0]) / (1e-3 + np.abs(b[0]))) < 1e-6        # five sweeps later still the same chain
     assert np.mean(np.all(np.abs(a[1] - b[1]) < 1e-9, axis=1)) > 0.99
+
+
+def test_cpo_from_stored_batches(tmp_path):
+    """ConditionalPredictiveOrdinates (src/PostProcessing.cpp:6330-6516) over the batch files the recorder wrote:
+    read with the reference's file layout, replayed on the device, compared with the oracle's dense
+    calcLikelihoodCPO on the same stored iterations."""
+    from bayesfmmm_b200 import io as bio
+    from bayesfmmm_b200 import post
+    s, eng, smp = _functional(seed=13, n=48)
+    r, thin = 10, 2
+    smp.record(str(tmp_path), r, thin)
+    for _ in range(2 * r):
+        smp.step(bf.SWEEP_FULL)
+    assert smp.batches_written == 2
+    cpo = post.conditional_predictive_ordinates(eng, str(tmp_path) + os.sep, 2, burnin_prop=0.3)
+    # the same computation through the oracle, from the same files
+    n, T = s["n"], s["T"]
+    d = orc.Data(n=n, K=s["K"], P=s["P"], M=s["M"], y=s["y"].ravel(), B=np.tile(s["B"], (n, 1)),
+                 off=np.arange(n + 1, dtype=np.int64) * T)
+    L = []
+    for q in range(2):
+        nu, Z, chi = (bio.load(str(tmp_path / f"{nm}{q}.txt")) for nm in ("Nu", "Z", "Chi"))
+        Phi, sig = bio.load(str(tmp_path / f"Phi{q}.txt")), bio.load(str(tmp_path / f"Sigma{q}.txt")).ravel()
+        for l in range(sig.size):
+            st = orc.State(nu=np.asfortranarray(nu[:, :, l]), Phi=np.asfortranarray(Phi[l, 0]), Z=np.asfortranarray(Z[:, :, l]),
+                           chi=np.asfortranarray(chi[:, :, l]), sigma_sq=float(sig[l]))
+            L.append(orc.marginal_loglik(d, st))
+    L = np.stack(L)
+    first = int(np.floor(0.3 * L.shape[0]))
+    assert np.max(np.abs(cpo - orc.cpo(L[first:])) / np.abs(cpo)) < 1e-10
+    smp.close(); eng.close()
