@@ -212,6 +212,8 @@ struct bfmmm_sampler {
   std::vector<std::vector<double>> pre_U;   // factors of the blocks' precisions computed in parallel ahead of the draws
   std::vector<char> pre_ok;
   std::vector<std::vector<double>> pre_Prec;  // per-thread scratch of prefactor_blocks
+  std::vector<std::vector<double>> pre_prior; // scaled penalty matrices of the nu / eta blocks (kept: 1.3 MB each at P = 400)
+  std::vector<double> prior_buf;
   int pre_next = -1;                        // next prefactored block (-1: none)
   int hbG = 0, hbP = 0;     // half bandwidths of the basis Gram and of the penalty matrix (block draws)
   const double* Hb = nullptr;   // ragged grids: pair cross-Gram band (set before the block draws)
@@ -290,6 +292,11 @@ void set_coef(bfmmm_sampler* s, int k, int mm, int dd, const double* in) {
 // basis of the high-dimensional model, P = 400) they are built and factorised on several host threads
 // before the sequential draws, which then only need the right-hand side and two triangular solves.
 struct PreBlock { int a; const double* prior_full; std::vector<double> prior_diag; };
+// out = c * A on the band |r - c| <= hb (the entries outside it are zero in A and stay zero in out)
+void scale_band(int n, int hb, double c, const double* A, double* out) {
+  for (int col = 0; col < n; col++)
+    for (int r = std::max(0, col - hb); r <= std::min(n - 1, col + hb); r++) out[(size_t)col * n + r] = c * A[(size_t)col * n + r];
+}
 constexpr int PREFACTOR_MIN_P = 96;
 void prefactor_blocks(bfmmm_sampler* s, const std::vector<PreBlock>& blocks, const double* WtW, double beta) {
   const int P = s->P, q = s->q, n = (int)blocks.size();
@@ -297,7 +304,7 @@ void prefactor_blocks(bfmmm_sampler* s, const std::vector<PreBlock>& blocks, con
   const double sc = beta / s->sigma_sq;
   const int hg = s->identity ? 0 : s->hbG;
   int nt = (int)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min(std::min(n, 8), nt > 1 ? nt / 2 : 1));
+  nt = std::max(1, std::min(std::min(n, 16), nt > 1 ? nt / 2 : 1));
   if ((int)s->pre_Prec.size() < nt) s->pre_Prec.resize(nt);
   auto work = [&](int t0, int stride) {
     std::vector<double>& Prec = s->pre_Prec[t0];     // only the band is written and read
@@ -902,19 +909,24 @@ int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtY
 int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   const int K = s->K, P = s->P;
   if (!s->zpre_on) s->rng.open(HP_NU);
-  vecd prior((size_t)P * P), diag(P);
-  std::vector<vecd> priors;
-  if (!s->ragged && P >= PREFACTOR_MIN_P) {
+  vecd diag(P);
+  const bool pre = !s->ragged && P >= PREFACTOR_MIN_P;
+  std::vector<vecd>& priors = s->pre_prior;            // persistent: no 1.3 MB allocations per sweep
+  if (!s->identity) {
+    if ((int)priors.size() < K) priors.resize(K);
+    for (int j = 0; j < K; j++) {
+      if (priors[j].size() < (size_t)P * P) priors[j].assign((size_t)P * P, 0.0);
+      scale_band(P, s->hbP, s->tau[j], s->Pmat.data(), priors[j].data());
+    }
+  }
+  if (pre) {
     std::vector<PreBlock> blocks;
-    if (!s->identity) priors.resize(K);
     for (int j = 0; j < K; j++) {
       if (s->identity) {
         PreBlock b{s->feat(j, 0, 0), nullptr, vecd(P)};
         for (int p = 0; p < P; p++) b.prior_diag[p] = 1 / s->tau[j];
         blocks.push_back(std::move(b));
       } else {
-        priors[j].resize((size_t)P * P);
-        for (size_t e = 0; e < priors[j].size(); e++) priors[j][e] = s->tau[j] * s->Pmat[e];
         blocks.push_back(PreBlock{s->feat(j, 0, 0), priors[j].data(), vecd()});
       }
     }
@@ -927,8 +939,7 @@ int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW
       for (int p = 0; p < P; p++) diag[p] = 1 / s->tau[j];
       rc = block_draw(s, j, 0, 0, WtW, BtYW, beta, nullptr, diag.data());
     } else {
-      for (size_t e = 0; e < prior.size(); e++) prior[e] = s->tau[j] * s->Pmat[e];
-      rc = block_draw(s, j, 0, 0, WtW, BtYW, beta, prior.data(), nullptr);
+      rc = block_draw(s, j, 0, 0, WtW, BtYW, beta, priors[j].data(), nullptr);
     }
   }
   s->pre_next = -1;
@@ -938,14 +949,16 @@ int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW
 int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   const int K = s->K, P = s->P, D = s->D;
   s->rng.open(HP_ETA);
-  vecd prior((size_t)P * P), diag(P);
+  vecd& prior = s->prior_buf;
+  if (prior.size() < (size_t)P * P) prior.assign((size_t)P * P, 0.0);
+  vecd diag(P);
   for (int d = 0; d < D; d++)
     for (int j = 0; j < K; j++) {
       if (s->identity) {
         for (int p = 0; p < P; p++) diag[p] = 1 / s->tau_eta_(j, d);
         if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, nullptr, diag.data())) return 1;
       } else {
-        for (size_t e = 0; e < prior.size(); e++) prior[e] = s->tau_eta_(j, d) * s->Pmat[e];
+        for (size_t e = 0; e < (size_t)P * P; e++) prior[e] = s->tau_eta_(j, d) * s->Pmat[e];
         if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, prior.data(), nullptr)) return 1;
       }
     }
