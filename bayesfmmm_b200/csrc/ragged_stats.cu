@@ -25,29 +25,24 @@ __device__ __forceinline__ void dmma884r(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+// Work layout: the output (band rows x feature pairs) is cut into S = gy * gz slices of RS_MTB m-tiles x NTB
+// pair-tiles (what one warp can accumulate in registers); the EIGHT WARPS of a block take eight different
+// slices of the SAME 8-function chunk, so the feature weights of a chunk are formed once per block
+// (cooperatively, into double-buffered shared memory) instead of once per slice -- the first version
+// recomputed them in every warp: 546 instructions per warp and chunk for 40 MMAs, DMMA pipe 38 % busy.
+// The base rows (Z, chi, X) of the next chunk are fetched into a register while the current one is consumed.
 template <int NTB>
-__global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const RaggedStatsArgs a) {
+__global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const RaggedStatsArgs a, int gy, int gz) {
   constexpr int TILES = RS_MTB * NTB;
-  __shared__ double s_acc[TILES * 64];
-  __shared__ double s_w[RS_WARPS][RS_QMAX][8];
-  __shared__ double s_base[RS_WARPS][RS_BASEMAX][8];
+  __shared__ double s_w[2][RS_QMAX][8];
+  __shared__ double s_base[2][RS_BASEMAX][8];
   __shared__ uchar4 s_feat[RS_QMAX];          // feature -> rows of s_base: (Z row, chi row or 255, X row or 255)
-  __shared__ unsigned char s_pa[NTB * 8], s_pb[NTB * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, c = lane & 3;
   const int rows = a.bw * a.P;
-  const int pair0 = blockIdx.z * NTB * 8;
-  // pair table of this block's slice: index -> (a, b), a <= b, row-major upper triangle
-  if (threadIdx.x < NTB * 8) {
-    int pf = pair0 + threadIdx.x, fa = 0;
-    unsigned char pa = 255, pb = 255;
-    if (pf < a.npairs) {
-      int rem = pf;
-      while (rem >= a.q - fa) { rem -= a.q - fa; fa++; }
-      pa = (unsigned char)fa; pb = (unsigned char)(fa + rem);
-    }
-    s_pa[threadIdx.x] = pa; s_pb[threadIdx.x] = pb;
-  }
+  const int sid = blockIdx.y * RS_WARPS + warp;            // this warp's slice
+  const bool active = sid < gy * gz;
+  const int ys = sid % gy, zs = sid / gy;
   if (threadIdx.x < a.q) {
     const int f = threadIdx.x;
     const int dd = f % (1 + a.D), km = f / (1 + a.D), mm = km % (a.M + 1), k = km / (a.M + 1);
@@ -55,80 +50,86 @@ __global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const Ragge
                             dd > 0 ? (unsigned char)(a.K + a.M + dd - 1) : 255, 0);
   }
   const int nbase = a.K + a.M + a.D;
-  __syncthreads();
+  // pair (fa <= fb) of this lane in each pair-tile: index -> row-major upper triangle
+  int pa[NTB], pb[NTB];
+#pragma unroll
+  for (int nt = 0; nt < NTB; nt++) {
+    int pf = (zs * NTB + nt) * 8 + g, fa = 0;
+    pa[nt] = 255; pb[nt] = 255;
+    if (active && pf < a.npairs) {
+      int rem = pf;
+      while (rem >= a.q - fa) { rem -= a.q - fa; fa++; }
+      pa[nt] = fa; pb[nt] = fa + rem;
+    }
+  }
   const double* ap[RS_MTB];
 #pragma unroll
   for (int mt = 0; mt < RS_MTB; mt++) {
-    int e = (blockIdx.y * RS_MTB + mt) * 8 + g;
-    ap[mt] = (e < rows) ? a.Gl + (size_t)e * a.ld : nullptr;
+    int e = (ys * RS_MTB + mt) * 8 + g;
+    ap[mt] = (active && e < rows) ? a.Gl + (size_t)e * a.ld : nullptr;
   }
-  int pa[NTB], pb[NTB];
-#pragma unroll
-  for (int nt = 0; nt < NTB; nt++) { pa[nt] = s_pa[nt * 8 + g]; pb[nt] = s_pb[nt * 8 + g]; }
-
   double R[RS_MTB][NTB][2];
 #pragma unroll
   for (int mt = 0; mt < RS_MTB; mt++)
 #pragma unroll
     for (int nt = 0; nt < NTB; nt++) { R[mt][nt][0] = 0; R[mt][nt][1] = 0; }
 
+  // staging role of this thread: element (row, slot) of the base rows
+  const int srow = threadIdx.x >> 3, slot = threadIdx.x & 7;
+  const double* ssrc = nullptr;
+  if (srow < nbase)
+    ssrc = srow < a.K ? a.Z + (size_t)srow * a.ld : (srow < a.K + a.M ? a.chi + (size_t)(srow - a.K) * a.ld : a.X + (size_t)(srow - a.K - a.M) * a.ld);
   const int n_chunks = a.ld >> 3;
-  const int wstride = gridDim.x * RS_WARPS;
-  const int slot = lane & 7;
-  for (int ch = blockIdx.x * RS_WARPS + warp; ch < n_chunks; ch += wstride) {
+  int ch = blockIdx.x;
+  double nextv = (ssrc && ch < n_chunks) ? ssrc[(ch << 3) + slot] : 0.0;
+  __syncthreads();
+  for (int it = 0; ch < n_chunks; ch += gridDim.x, it++) {
+    const int buf = it & 1;
     const int i8 = ch << 3;
+    if (ssrc) s_base[buf][srow][slot] = nextv;
     double2 av[RS_MTB];
 #pragma unroll
     for (int mt = 0; mt < RS_MTB; mt++)
       av[mt] = ap[mt] ? __ldcs(reinterpret_cast<const double2*>(ap[mt] + i8 + 2 * c)) : make_double2(0.0, 0.0);
-    // feature weights of the 8 functions of this chunk: w[f][slot].  The K + M + D base rows are staged
-    // once (two loads per lane), the products are formed from shared memory with the feature -> (k, m, d)
-    // table built at block start (no integer division in the loop).
-    for (int r = lane >> 3; r < nbase; r += 4) {
-      const double* src = r < a.K ? a.Z + (size_t)r * a.ld : (r < a.K + a.M ? a.chi + (size_t)(r - a.K) * a.ld : a.X + (size_t)(r - a.K - a.M) * a.ld);
-      s_base[warp][r][slot] = src[i8 + slot];
-    }
-    __syncwarp();
-    for (int f = lane >> 3; f < a.q; f += 4) {
+    const int chn = ch + gridDim.x;
+    if (ssrc && chn < n_chunks) nextv = ssrc[(chn << 3) + slot];        // in flight while this chunk is consumed
+    __syncthreads();
+    for (int f = srow; f < a.q; f += RS_THREADS / 8) {                  // feature weights, once per block
       const uchar4 t = s_feat[f];
-      double w = s_base[warp][t.x][slot];
-      if (t.y != 255) w *= s_base[warp][t.y][slot];
-      if (t.z != 255) w *= s_base[warp][t.z][slot];
-      s_w[warp][f][slot] = w;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < NTB; nt++) {
-      double2 wv = make_double2(0.0, 0.0);
-      if (pa[nt] != 255) {
-        const double2 wa = *reinterpret_cast<const double2*>(&s_w[warp][pa[nt]][2 * c]);
-        const double2 wb = *reinterpret_cast<const double2*>(&s_w[warp][pb[nt]][2 * c]);
-        wv.x = wa.x * wb.x; wv.y = wa.y * wb.y;
-      }
-#pragma unroll
-      for (int mt = 0; mt < RS_MTB; mt++) {
-        dmma884r(R[mt][nt][0], R[mt][nt][1], av[mt].x, wv.x);
-        dmma884r(R[mt][nt][0], R[mt][nt][1], av[mt].y, wv.y);
-      }
-    }
-    __syncwarp();
-  }
-  for (int w = 0; w < RS_WARPS; w++) {
-    if (warp == w) {
-      int t = 0;
-#pragma unroll
-      for (int mt = 0; mt < RS_MTB; mt++)
-#pragma unroll
-        for (int nt = 0; nt < NTB; nt++, t++) {
-          int idx = t * 64 + g * 8 + 2 * c;
-          if (w == 0) { s_acc[idx] = R[mt][nt][0]; s_acc[idx + 1] = R[mt][nt][1]; }
-          else { s_acc[idx] += R[mt][nt][0]; s_acc[idx + 1] += R[mt][nt][1]; }
-        }
+      double w = s_base[buf][t.x][slot];
+      if (t.y != 255) w *= s_base[buf][t.y][slot];
+      if (t.z != 255) w *= s_base[buf][t.z][slot];
+      s_w[buf][f][slot] = w;
     }
     __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int nt = 0; nt < NTB; nt++) {
+        double2 wv = make_double2(0.0, 0.0);
+        if (pa[nt] != 255) {
+          const double2 wa = *reinterpret_cast<const double2*>(&s_w[buf][pa[nt]][2 * c]);
+          const double2 wb = *reinterpret_cast<const double2*>(&s_w[buf][pb[nt]][2 * c]);
+          wv.x = wa.x * wb.x; wv.y = wa.y * wb.y;
+        }
+#pragma unroll
+        for (int mt = 0; mt < RS_MTB; mt++) {
+          dmma884r(R[mt][nt][0], R[mt][nt][1], av[mt].x, wv.x);
+          dmma884r(R[mt][nt][0], R[mt][nt][1], av[mt].y, wv.y);
+        }
+      }
+    }
   }
-  double* row = a.partials + (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (TILES * 64);
-  for (int idx = threadIdx.x; idx < TILES * 64; idx += RS_THREADS) row[idx] = s_acc[idx];
+  if (!active) return;
+  // every warp owns its slice: straight from the accumulators to this block's partial row
+  double* row = a.partials + (((size_t)zs * gy + ys) * gridDim.x + blockIdx.x) * (TILES * 64);
+  int t = 0;
+#pragma unroll
+  for (int mt = 0; mt < RS_MTB; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NTB; nt++, t++) {
+      const int idx = t * 64 + g * 8 + 2 * c;
+      row[idx] = R[mt][nt][0]; row[idx + 1] = R[mt][nt][1];
+    }
 }
 
 // one warp per output element Hb[pair][e]
@@ -157,7 +158,8 @@ static void rs_shape(int P, int bw, int q, int sm_count, int& NTB, int& gx, int&
   gz = (ptiles + NTB - 1) / NTB;
   int mtiles = (bw * P + 7) / 8;
   gy = (mtiles + RS_MTB - 1) / RS_MTB;
-  gx = (2 * sm_count) / (gy * gz);       // two blocks per SM, ONE wave (rounding up left a 6 % second wave: 2x the time)
+  const int yblocks = (gy * gz + RS_WARPS - 1) / RS_WARPS;     // blocks of eight slices
+  gx = (2 * sm_count) / yblocks;         // two blocks per SM, ONE wave
   if (gx < 1) gx = 1;
 }
 
@@ -169,8 +171,8 @@ size_t ragged_stats_partial_doubles(int P, int bw, int q, int sm_count) {
 
 template <int NTB>
 static int launch_rs(const RaggedStatsArgs& a, int gx, int gy, int gz, cudaStream_t s) {
-  dim3 grid(gx, gy, gz);
-  ragged_stats_kernel<NTB><<<grid, RS_THREADS, 0, s>>>(a);
+  dim3 grid(gx, (gy * gz + RS_WARPS - 1) / RS_WARPS);
+  ragged_stats_kernel<NTB><<<grid, RS_THREADS, 0, s>>>(a, gy, gz);
   int64_t tot = (int64_t)a.npairs * a.bw * a.P;
   ragged_stats_final_kernel<NTB><<<(unsigned)((tot + 7) / 8), 256, 0, s>>>(a, gx, gy);
   g_launch_count += 2;
