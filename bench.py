@@ -229,23 +229,34 @@ def run_ours(a):
                 off = (p - ptr) // 8
                 dist.all_reduce(stats_t[off:off + l])
             smp.set_allreduce(allreduce)
-        elif not os.environ.get("BFMMM_P2P_ALLREDUCE"):
+        else:
             def exchange_id(idb):
                 t = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", local))
                 if rank == 0:
                     t.copy_(torch.frombuffer(bytearray(idb), dtype=torch.uint8))
                 dist.broadcast(t, 0)
                 return bytes(t.cpu().numpy().tobytes())
-            smp.enable_nccl(rank, world, exchange_id)
-        else:
-            # BFMMM_P2P_ALLREDUCE=1: one-shot all-reduce over NVLink peer memory (csrc/p2p_hook.cu); the IPC handles
-            # of the mailboxes are all-gathered through the process group (measured equal to NCCL at 2 ranks)
+
             def allgather(h):
                 mine = torch.frombuffer(bytearray(h), dtype=torch.uint8).to(torch.device("cuda", local))
                 out = [torch.zeros(64, dtype=torch.uint8, device=torch.device("cuda", local)) for _ in range(world)]
                 dist.all_gather(out, mine)
                 return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
-            smp.enable_p2p(rank, world, eng.stats_buffer()[1], allgather)
+            # From 4 ranks on: one-shot all-reduce over NVLink peer memory (csrc/p2p_hook.cu; measured at 8 ranks
+            # 0.399 ms per sweep against 0.415 ms with ncclAllReduce; at 2 ranks 0.357 against 0.348, so NCCL stays
+            # there).  BFMMM_NCCL_ALLREDUCE=1 / BFMMM_P2P_ALLREDUCE=1 force one or the other; a failed peer
+            # mapping on any rank selects the native NCCL hook (csrc/nccl_hook.cu).
+            use_p2p = (world >= 4 or bool(os.environ.get("BFMMM_P2P_ALLREDUCE"))) and not os.environ.get("BFMMM_NCCL_ALLREDUCE")
+            ok = torch.ones(1, device=torch.device("cuda", local))
+            if use_p2p:
+                try:
+                    smp.enable_p2p(rank, world, eng.stats_buffer()[1], allgather)
+                except Exception as exc:          # no peer access between some pair of devices
+                    print(f"rank {rank}: peer-memory all-reduce unavailable ({exc}); using NCCL", file=sys.stderr)
+                    ok.zero_()
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if not use_p2p or ok.item() == 0:
+                smp.enable_nccl(rank, world, exchange_id)
             dist.barrier()
 
     def barrier():
