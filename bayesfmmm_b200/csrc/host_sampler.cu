@@ -709,7 +709,7 @@ int bfmmm_host_update_tau(bfmmm_sampler* s) {
     for (int r = 0; r < P; r++) {
       double pr = 0;
       if (s->identity) pr = s->nu_(k, r);
-      else for (int c = 0; c < P; c++) pr += s->Pmat[(size_t)c * P + r] * s->nu_(k, c);
+      else for (int c = std::max(0, r - s->hbP); c <= std::min(P - 1, r + s->hbP); c++) pr += s->Pmat[(size_t)r * P + c] * s->nu_(k, c);   // banded, symmetric
       quad += s->nu_(k, r) * pr;
     }
     double b = s->h.beta_nu + 0.5 * quad;
@@ -730,7 +730,7 @@ int bfmmm_host_update_tau_eta(bfmmm_sampler* s) {
       for (int r = 0; r < P; r++) {
         double pr = 0;
         if (s->identity) pr = s->eta_(r, d, j);
-        else for (int c = 0; c < P; c++) pr += s->Pmat[(size_t)c * P + r] * s->eta_(c, d, j);
+        else for (int c = std::max(0, r - s->hbP); c <= std::min(P - 1, r + s->hbP); c++) pr += s->Pmat[(size_t)r * P + c] * s->eta_(c, d, j);
         quad += s->eta_(r, d, j) * pr;
       }
       double b = s->h.beta_eta + 0.5 * quad;
@@ -958,7 +958,7 @@ int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtY
         for (int p = 0; p < P; p++) diag[p] = 1 / s->tau_eta_(j, d);
         if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, nullptr, diag.data())) return 1;
       } else {
-        for (size_t e = 0; e < (size_t)P * P; e++) prior[e] = s->tau_eta_(j, d) * s->Pmat[e];
+        scale_band(P, s->hbP, s->tau_eta_(j, d), s->Pmat.data(), prior.data());
         if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, prior.data(), nullptr)) return 1;
       }
     }
