@@ -19,6 +19,8 @@
 #include "../../include/bfmmm_sampler.h"
 #include "common.cuh"
 
+namespace bf_host { bool chol_upper_rev(int n, const double* A, double* U, int hb); }
+
 namespace {
 
 // ------------------------------------------------------------------ host random numbers
@@ -109,25 +111,8 @@ bool chol_rows(int n, const double* A, double* L) {
 // matrix has the same band, so B-spline Gram + tridiagonal penalty + diagonal shrinkage priors cost
 // O(n hb^2) instead of O(n^3 / 3): at P = 20 (cubic, hb = 3) 180 instead of 2700 flops per block, at
 // P = 400 (tensor basis, hb = 63) 13x fewer.  Skipped terms are exact zeros, so the result is the dense one.
-bool chol_upper_rev(int n, const double* A, double* U, int hb) {
-  for (int j = n - 1; j >= 0; j--) {
-    double* uj = U + (size_t)j * n;
-    const int kj = std::min(n - 1, j + hb);
-    double s = A[(size_t)j * n + j];
-    for (int k = j + 1; k <= kj; k++) s -= uj[k] * uj[k];
-    if (!(s > 0)) return false;
-    const double d = std::sqrt(s);
-    uj[j] = d;
-    for (int i = std::max(0, j - hb); i < j; i++) {
-      double* ui = U + (size_t)i * n;
-      double t = A[(size_t)j * n + i];
-      const int ki = std::min(n - 1, i + hb);
-      for (int k = j + 1; k <= ki; k++) t -= ui[k] * uj[k];
-      ui[j] = t / d;
-    }
-  }
-  return true;
-}
+// (implemented in host_linalg.cpp: baseline and AVX2+FMA clones of the same loops, selected at run time)
+bool chol_upper_rev(int n, const double* A, double* U, int hb) { return bf_host::chol_upper_rev(n, A, U, hb); }
 // x = U^{-T} (U^{-1} b + z)
 void draw_from_rev_chol(int n, const double* U, const double* b, const double* z, double* x, double* w, int hb) {
   for (int i = n - 1; i >= 0; i--) {                 // U w = b
