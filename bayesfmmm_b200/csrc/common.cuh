@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace bf {
 
 constexpr int DMAX = 4;         // covariates supported by the covariate-adjusted kernels
@@ -29,15 +31,15 @@ struct PassArgs {
   int bw;                           // ragged grids: band width (degree + 1)
   const double* __restrict__ rss;
   double* __restrict__ Z;
-  double* __restrict__ lZ;          // log Z [K][ld], kept next to Z by every writer of Z (set_state, Z step, restore)
   double* __restrict__ chi;
   const double* __restrict__ X;
   const double* __restrict__ glob;
   double sigma_sq, beta;
   const double* __restrict__ sigma_dev;   // chi: sigma^2 drawn on the device by sigma_draw_kernel (nullptr: use sigma_sq)
   // Z step
-  double alpha3, a_Z_PM, log_a_Z_PM;
-  double lgam_a, digam_a, trigam_a; // log Gamma, digamma, trigamma at a_Z_PM (host): lgamma(a sum_k z_k) by its Taylor series
+  double alpha3, a_Z_PM, log_a_Z_PM, inv_a_Z_PM;
+  double c_tot, trigam_a;           // 1 - log a + digamma(a) and trigamma(a) at a = a_Z_PM (host): lgamma(a sum_k z*_k) - lgamma(a sum_k z_k)
+                                    // by its Taylor series around a, merged with the Stirling main terms (z_logratio_closed)
   double pi[8];
   const double* __restrict__ gam;   // injected draws [K][ld] or nullptr (device RNG)
   const double* __restrict__ u;     // [ld] or nullptr
@@ -53,6 +55,7 @@ struct PassArgs {
   int cpo_first;
   // RNG
   uint64_t key, iteration, global_offset;
+  uint32_t rk[20];                  // Philox round keys (k0 + r W0, k1 + r W1), r = 0..9: read as constant operands
   // reduction
   double* __restrict__ partials;    // [gridDim.x][RED_MAX]
   unsigned int* __restrict__ ticket;
@@ -191,12 +194,28 @@ __device__ __forceinline__ void philox_words(uint64_t key, uint64_t index, uint6
   Philox::block(c, (uint32_t)key, (uint32_t)(key >> 32));
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
+// The same block with the ten round keys taken from the kernel parameters (host: philox_round_keys): two
+// IMAD.WIDE and two LOP3 per round, the key schedule costs nothing per function.
+__device__ __forceinline__ void philox_rk(const PassArgs& a, uint64_t index, uint32_t purpose, uint32_t block, uint32_t (&out)[4]) {
+  uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = (uint32_t)(a.iteration * 64 + purpose), c3 = block;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a.rk[2 * r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ a.rk[2 * r + 1];
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
   uint64_t a = ((uint64_t)hi << 32) | lo;
   return ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 __device__ __forceinline__ double u32(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 #endif
+inline void philox_round_keys(uint64_t key, uint32_t (&rk)[20]) {
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  for (int r = 0; r < 10; r++) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
 enum { RNG_Z_PROPOSAL = 1, RNG_Z_ACCEPT = 2, RNG_CHI = 3, RNG_Z_PROPOSAL_SLOW = 4 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -330,6 +349,6 @@ int launch_sigma_draw(const double* ssr_dev, double a, double scale_ssr, double 
                       uint32_t purpose, double* sigma_dev, double* host_mapped, double seq, cudaStream_t s);
 int launch_log_rows(const double* src, double* dst, size_t count, cudaStream_t s);   // dst = log(src), elementwise
 
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library (all engines, all host threads)
 int set_error(const char* msg);   // records the message returned by bfmmm_last_error(); returns 1
 }  // namespace bf

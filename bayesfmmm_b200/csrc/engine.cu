@@ -13,7 +13,7 @@
 #include "../../include/bfmmm.h"
 #include "common.cuh"
 
-namespace bf { unsigned long long g_launch_count = 0; }
+namespace bf { std::atomic<unsigned long long> g_launch_count{0}; }
 
 namespace {
 thread_local std::string g_err;
@@ -42,11 +42,11 @@ struct bfmmm_engine {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   // device
-  double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *lZ = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
+  double *Ct = nullptr, *rss = nullptr, *Z = nullptr, *chi = nullptr, *X = nullptr, *glob = nullptr;
   double *Hh = nullptr, *Gl = nullptr, *rs_partials = nullptr;   // ragged grids: B_i'y_i, band of G_i
   int bw = 0, npairs = 0;
   bool ragged = false;
-  double *snapZ = nullptr, *snapLZ = nullptr, *snapChi = nullptr;   // device copy of (Z, log Z, chi) for tempered transitions
+  double *snapZ = nullptr, *snapChi = nullptr;   // device copy of (Z, chi) for tempered transitions
   double *ni = nullptr;                          // ragged grids: points per function (marginal log-likelihood)
   double *cpo_m = nullptr, *cpo_s = nullptr, *logl = nullptr;   // CPO accumulators, per-function marginal log-likelihood
   int64_t cpo_count = 0;
@@ -104,9 +104,9 @@ bool chol_lower(int n, const std::vector<double>& A, std::vector<double>& L) {
 void free_all(bfmmm_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->lZ); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
+  cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
   cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
-  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapLZ); cudaFree(e->snapChi);
+  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi);
   cudaFree(e->Hh); cudaFree(e->Gl); cudaFree(e->rs_partials);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->ev_snap) cudaEventDestroy(e->ev_snap);
@@ -328,7 +328,7 @@ int project_ragged(bfmmm_engine* e, const bfmmm_config* c) {
 extern "C" {
 
 const char* bfmmm_last_error(void) { return g_err.c_str(); }
-int64_t bfmmm_launch_count(void) { return (int64_t)bf::g_launch_count; }
+int64_t bfmmm_launch_count(void) { return (int64_t)bf::g_launch_count.load(); }
 
 int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   if (!c || !out) return fail("bfmmm_create: null argument");
@@ -358,6 +358,17 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, c->device);
   e->sm_count = prop.multiProcessorCount;
+  {
+    // the pass kernels stage the whitened globals (P4 x QS doubles) in shared memory next to ~6 KB of static tables
+    const size_t need = (size_t)((e->P + 3) & ~3) * e->QS * 8 + 6 * 1024;
+    if (need > (size_t)prop.sharedMemPerBlockOptin) {
+      const int q = e->q;
+      delete e;
+      return fail("bfmmm_create: P * q = " + std::to_string(c->P) + " * " + std::to_string(q) +
+                  " doubles of global coefficients do not fit the " + std::to_string(prop.sharedMemPerBlockOptin / 1024) +
+                  " KB of shared memory per block (need P4 * q * 8 + 6 KB; q = K (1 + D)(1 + M))");
+    }
+  }
   auto bail = [&](int) { free_all(e); return 1; };
 #define CUE(x)                                                                  \
   do {                                                                          \
@@ -370,7 +381,6 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMalloc(&e->Ct, ld * e->P4 * 8));
   CUE(cudaMalloc(&e->rss, ld * 8));
   CUE(cudaMalloc(&e->Z, ld * e->K * 8));
-  CUE(cudaMalloc(&e->lZ, ld * e->K * 8));
   CUE(cudaMalloc(&e->chi, ld * e->M * 8));
   if (e->D) CUE(cudaMalloc(&e->X, ld * e->D * 8));
   CUE(cudaMalloc(&e->glob, (size_t)e->P4 * e->QS * 8));
@@ -387,7 +397,6 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMemsetAsync(e->Ct, 0, ld * e->P4 * 8, e->stream));
   CUE(cudaMemsetAsync(e->rss, 0, ld * 8, e->stream));
   CUE(cudaMemsetAsync(e->Z, 0, ld * e->K * 8, e->stream));
-  if (bf::launch_log_rows(e->Z, e->lZ, ld * e->K, e->stream)) { fail("log kernel launch failed"); return bail(1); }
   CUE(cudaMemsetAsync(e->chi, 0, ld * e->M * 8, e->stream));
   CUE(cudaMemsetAsync(e->stats, 0, e->stats_len * 8, e->stream));
   CUE(cudaMemsetAsync(e->draws, 0, ld * (std::max(e->K + 1, e->M)) * 8, e->stream));
@@ -470,7 +479,6 @@ int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   if (Z && upload_cols(e, e->Z, Z, e->K)) return 1;
-  if (Z && bf::launch_log_rows(e->Z, e->lZ, (size_t)e->ld * e->K, e->stream)) return fail("log kernel launch failed");
   if (chi && upload_cols(e, e->chi, chi, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
   return 0;
@@ -574,9 +582,10 @@ static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
   a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.D = e->D; a.QS = e->QS; a.P4 = (e->Pc + 3) & ~3;
   a.sm_count = e->sm_count; a.max_blocks = e->pass_blocks;
-  a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.lZ = e->lZ; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
+  a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
   a.sigma_sq = e->sigma_sq; a.beta = beta;
   a.key = e->key; a.iteration = e->iteration; a.global_offset = (uint64_t)e->global_offset;
+  bf::philox_round_keys(e->key, a.rk);
   a.partials = e->partials; a.ticket = e->ticket;
 }
 
@@ -594,8 +603,10 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
                     bool dump_draws) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
-  a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM);
-  a.lgam_a = std::lgamma(a_Z_PM); polygamma01(a_Z_PM, a.digam_a, a.trigam_a);
+  a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM); a.inv_a_Z_PM = 1.0 / a_Z_PM;
+  double digam_a = 0;
+  polygamma01(a_Z_PM, digam_a, a.trigam_a);
+  a.c_tot = 1.0 - a.log_a_Z_PM + digam_a;
   for (int k = 0; k < e->K; k++) a.pi[k] = pi[k];
 #ifdef BF_TUNE_V
   static const bool force_inject = std::getenv("BFMMM_Z_INJECT") != nullptr;   // tuning: time the step without the RNG
@@ -813,10 +824,8 @@ int bfmmm_state_snapshot(bfmmm_engine* e) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   if (!e->snapZ) CU(cudaMalloc(&e->snapZ, (size_t)e->ld * e->K * 8));
-  if (!e->snapLZ) CU(cudaMalloc(&e->snapLZ, (size_t)e->ld * e->K * 8));
   if (!e->snapChi) CU(cudaMalloc(&e->snapChi, (size_t)e->ld * e->M * 8));
   CU(cudaMemcpyAsync(e->snapZ, e->Z, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
-  CU(cudaMemcpyAsync(e->snapLZ, e->lZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
   CU(cudaMemcpyAsync(e->snapChi, e->chi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
@@ -824,7 +833,6 @@ int bfmmm_state_restore(bfmmm_engine* e) {
   if (!e || !e->snapZ) return fail("bfmmm_state_restore: no snapshot");
   CU(cudaSetDevice(e->device));
   CU(cudaMemcpyAsync(e->Z, e->snapZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
-  CU(cudaMemcpyAsync(e->lZ, e->snapLZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
   CU(cudaMemcpyAsync(e->chi, e->snapChi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }

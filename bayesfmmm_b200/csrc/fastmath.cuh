@@ -70,6 +70,38 @@ __device__ __forceinline__ double fast_log(double x) {
   return fma(e, FM_STI[6], t.y) + fma(p * r, r, r);
 }
 
+// the same without the range check: the caller guarantees a positive, finite, normal argument (uniforms, ratios)
+__device__ __forceinline__ double fast_log_pos(double x) {
+  const double2* tbl = fm_log_table();
+  const int hi = __double2hiint(x);
+  const double2 t = tbl[(hi >> 13) & (FM_LOG_TBL - 1)];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double r = fma(m, t.x, -1.0);
+  const double e = (double)((hi >> 20) - 1023);
+  double p = fma(r, FM_LOG[5], FM_LOG[4]);
+  p = fma(p, r, FM_LOG[3]); p = fma(p, r, FM_LOG[2]); p = fma(p, r, FM_LOG[1]); p = fma(p, r, FM_LOG[0]);
+  return fma(e, FM_STI[6], t.y) + fma(p * r, r, r);
+}
+
+// exp(x) for x <= 0 (0 below -700): x = k log 2 + r, |r| <= log(2)/2; exp(r) by its Taylor series to r^13 (remainder
+// < 5e-18), scaled by 2^k through the exponent field.  Relative error < 3e-16.
+static __constant__ double FM_EXP[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                         1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__device__ __forceinline__ double fast_exp_nonpos(double x) {
+  const double xc = x > -700.0 ? x : -700.0;
+  const double t = fma(xc, 1.4426950408889634074, 6755399441055744.0);      // round(x / log 2) in the low word
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -0.693147180559945286, xc);
+  r = fma(kf, -2.319046813846299558e-17, r);
+  double p = fma(r, FM_EXP[0], FM_EXP[1]);
+#pragma unroll
+  for (int j = 2; j < 12; j++) p = fma(p, r, FM_EXP[j]);
+  p = fma(p * r, r, r) + 1.0;                                                // 1 + r + r^2 (1/2 + ...)
+  const double s = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return x > -700.0 ? s : 0.0;
+}
+
 // 1/x and 1/sqrt(x), sqrt(x): MUFU seed (about 20 bits) + two Newton steps; x positive finite normal,
 // result normal.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -79,6 +111,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
   return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rcp1(double x) {             // one Newton step: about 40 bits
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return fma(y, fma(-x, y, 1.0), y);
 }
 __device__ __forceinline__ double fast_rsqrt_seed1(double x) {      // one Newton step: about 40 bits
   double y;
@@ -125,7 +162,7 @@ __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
 
 // two independent standard normals from three words (Box-Muller)
 __device__ __forceinline__ void fast_box_muller(uint32_t w0, uint32_t w1, uint32_t w2, double& n0, double& n1) {
-  const double r = fast_sqrt(-2.0 * fast_log(u52(w0, w1)));
+  const double r = fast_sqrt(-2.0 * fast_log_pos(u52(w0, w1)));      // u52 is in [2^-53, 1): positive and normal
   double cs, sn;
   sincos_u32(w2, cs, sn);
   n0 = r * cs; n1 = r * sn;
@@ -137,6 +174,13 @@ __device__ __forceinline__ double stirling16(double x, double lx) {
   double s = fma(r2, FM_STI[4], FM_STI[3]);
   s = fma(r2, s, FM_STI[2]); s = fma(r2, s, FM_STI[1]); s = fma(r2, s, FM_STI[0]);
   return fma(x - 0.5, lx, -x) + fma(r, s, FM_STI[5]);
+}
+// S(r) = lgamma(x) - [(x - 1/2) log x - x + log(2 pi)/2] at r = 1/x, x >= 16 (the series' next term is < 1.1e-16)
+__device__ __forceinline__ double stirling_corr(double r) {
+  const double r2 = r * r;
+  double s = fma(r2, FM_STI[4], FM_STI[3]);
+  s = fma(r2, s, FM_STI[2]); s = fma(r2, s, FM_STI[1]); s = fma(r2, s, FM_STI[0]);
+  return r * s;
 }
 // log Gamma(x), x > 0, with lx = log x known.  x < 16 is shifted: Gamma(x) = Gamma(x + 16) / (x (x+1) ... (x+15));
 // that branch is out of line (one copy per kernel instead of one per call site: the Z kernel is
@@ -159,15 +203,17 @@ static __device__ __noinline__ double fast_log_nl(double x) { return fast_log(x)
 // candidate g = d v and whether it is accepted (false with probability ~1e-3 at shape 10, ~1e-5 at
 // shape 3000: the caller then falls back to RngStream::gamma).  c = 1/sqrt(9d) only shapes the envelope
 // (any c gives an exact sampler as long as the same c is used in the test), so a 40-bit value is enough.
-__device__ __forceinline__ bool gamma_candidate_fast(double shape, double x, double uu, double& g) {
+// l3 receives 3 log(1 + c x) = log v (the Z step reuses it: log g = log d + l3).
+__device__ __forceinline__ bool gamma_candidate_fast(double shape, double x, double uu, double& g, double& l3) {
   const double d = shape - 1.0 / 3.0;
   const double c = fast_rsqrt_seed1(9.0 * d);
   const double t = c * x;
   const double v1 = 1.0 + t;
   const double v = v1 * v1 * v1;
   g = d * v;
+  l3 = 0.0;
   if (t <= -0.99) return false;
-  const double l3 = 3.0 * (fabs(t) <= 0.03125 ? log1p_series(t) : fast_log_nl(v1));
+  l3 = 3.0 * (fabs(t) <= 0.03125 ? log1p_series(t) : fast_log_nl(v1));
   const double R = fma(0.5 * x, x, d * (1.0 - v + l3));
   bool ok = (uu - 1.0 < R);
   if (!ok) ok = fast_log_nl(uu) < R;

@@ -32,10 +32,11 @@ struct HostRng {
   uint64_t key = 0, iteration = 0;
   std::deque<double> tape;
   bool use_tape = false;
+  bool tape_underrun = false;      // an update asked for more injected draws than the tape held: the caller fails
   bf::RngStream stream{0, 0, 0, 0};
   void open(uint32_t purpose) { stream = bf::RngStream(key, 0xB200ull, iteration, purpose); }
   double pop() {
-    if (tape.empty()) return std::numeric_limits<double>::quiet_NaN();
+    if (tape.empty()) { tape_underrun = true; return std::numeric_limits<double>::quiet_NaN(); }
     double v = tape.front(); tape.pop_front(); return v;
   }
   double normal() { return use_tape ? pop() : stream.normal(); }
@@ -249,6 +250,31 @@ struct bfmmm_sampler {
 };
 
 namespace {
+
+// an update that asked for more injected draws than the tape held has produced NaNs: fail instead of returning them
+int tape_check(bfmmm_sampler* s) {
+  if (!s->rng.tape_underrun) return 0;
+  s->rng.tape_underrun = false;
+  return sfail("the tape of injected draws ran out (bfmmm_sampler_tape holds fewer values than the update consumes)");
+}
+
+// the chain's global parameters: what a rejected tempered transition restores (BFMMM.h:1631-1651)
+struct ChainParams {
+  vecd nu, Phi, pi, delta, gamma, A, tau, eta, xi, tau_eta, delta_xi, gamma_xi, A_xi;
+  double sigma_sq, alpha3, loglik, last_ssr, ll_sigma;
+  bool ll_pending;
+  int64_t last_accept;
+};
+ChainParams save_params(const bfmmm_sampler* s) {
+  return ChainParams{s->nu, s->Phi, s->pi, s->delta, s->gamma, s->A, s->tau, s->eta, s->xi, s->tau_eta, s->delta_xi, s->gamma_xi,
+                     s->A_xi, s->sigma_sq, s->alpha3, s->loglik, s->last_ssr, s->ll_sigma, s->ll_pending, s->last_accept};
+}
+void restore_params(bfmmm_sampler* s, const ChainParams& c) {
+  s->nu = c.nu; s->Phi = c.Phi; s->pi = c.pi; s->delta = c.delta; s->gamma = c.gamma; s->A = c.A; s->tau = c.tau;
+  s->eta = c.eta; s->xi = c.xi; s->tau_eta = c.tau_eta; s->delta_xi = c.delta_xi; s->gamma_xi = c.gamma_xi; s->A_xi = c.A_xi;
+  s->sigma_sq = c.sigma_sq; s->alpha3 = c.alpha3; s->loglik = c.loglik; s->last_ssr = c.last_ssr; s->ll_sigma = c.ll_sigma;
+  s->ll_pending = c.ll_pending; s->last_accept = c.last_accept;
+}
 
 // coefficient vector of feature f (length P) read from / written to the sampler state
 void get_coef(bfmmm_sampler* s, int k, int mm, int dd, double* out) {
@@ -661,7 +687,7 @@ int bfmmm_host_update_pi(bfmmm_sampler* s, const double* slz) {
   double acc = lnew - lold + q_old - q_new;
   double u = s->rng.uniform();
   if (std::log(u) < acc) s->pi = prop;
-  return 0;
+  return tape_check(s);
 }
 
 // updateAlpha3 (UpdateAlpha3.h:36-63, lpdf_alpha3 :10-26)
@@ -681,7 +707,7 @@ int bfmmm_host_update_alpha3(bfmmm_sampler* s, const double* slz) {
   double lold = lpdf(s->alpha3, prop), lnew = lpdf(prop, s->alpha3);
   double u = s->rng.uniform();
   if (std::log(u) < lnew - lold) s->alpha3 = prop;
-  return 0;
+  return tape_check(s);
 }
 
 // updateTau (UpdateTau.h:18-40) / updateTauMV (:47-68): note the integer division nu.n_cols / 2
@@ -701,7 +727,7 @@ int bfmmm_host_update_tau(bfmmm_sampler* s) {
     double g = (1 / b) * s->rng.gamma(a);
     s->tau[k] = s->identity ? 1 / g : g;
   }
-  return 0;
+  return tape_check(s);
 }
 
 // updateTauEta (UpdateTau.h:75-99) / updateTauEtaMV (:106-128)
@@ -722,7 +748,7 @@ int bfmmm_host_update_tau_eta(bfmmm_sampler* s) {
       double g = (1 / b) * s->rng.gamma(a);
       s->tau_eta_(j, d) = s->identity ? 1 / g : g;
     }
-  return 0;
+  return tape_check(s);
 }
 
 // updateDelta (UpdateDelta.h:17-66): multiplicative gamma process shrinkage
@@ -753,7 +779,7 @@ int bfmmm_host_update_delta(bfmmm_sampler* s) {
       }
       s->delta_(k, i) = (1 / p2) * s->rng.gamma(p1);
     }
-  return 0;
+  return tape_check(s);
 }
 
 // updateDeltaXi (UpdateDelta.h:76-125)
@@ -785,7 +811,7 @@ int bfmmm_host_update_delta_xi(bfmmm_sampler* s) {
         }
         s->delta_xi_(k, i, d) = (1 / p2) * s->rng.gamma(p1);
       }
-  return 0;
+  return tape_check(s);
 }
 
 // updateGamma (UpdateGamma.h:17-38)
@@ -802,7 +828,7 @@ int bfmmm_host_update_gamma(bfmmm_sampler* s) {
         s->gamma_(i, l, j) = scale * s->rng.gamma((nug + 1) / 2);
       }
     }
-  return 0;
+  return tape_check(s);
 }
 
 // updateGammaXi (UpdateGamma.h:48-72)
@@ -820,7 +846,7 @@ int bfmmm_host_update_gamma_xi(bfmmm_sampler* s) {
           s->gamma_xi_(k, l, i, j) = scale * s->rng.gamma((nug + 1) / 2);
         }
       }
-  return 0;
+  return tape_check(s);
 }
 
 static double lpdf_a1(double al, double be, double a, double delta) {          // UpdateA.h:17-23
@@ -848,7 +874,7 @@ int bfmmm_host_update_A(bfmmm_sampler* s) {
   s->rng.open(HP_A);
   for (int j = 0; j < s->K; j++)
     for (int i = 0; i < 2; i++) mh_a(s, s->A_(j, i), i == 0, &s->delta_(j, 0), s->M, s->K);
-  return 0;
+  return tape_check(s);
 }
 // updateAXi (UpdateA.h:137-209): order j, i, d
 int bfmmm_host_update_A_xi(bfmmm_sampler* s) {
@@ -856,7 +882,7 @@ int bfmmm_host_update_A_xi(bfmmm_sampler* s) {
   for (int j = 0; j < s->K; j++)
     for (int i = 0; i < 2; i++)
       for (int d = 0; d < s->D; d++) mh_a(s, s->A_xi_(j, i, d), i == 0, &s->delta_xi_(j, 0, d), s->M, s->K);
-  return 0;
+  return tape_check(s);
 }
 
 // updatePhi (UpdatePhi.h:23-89): blocks (j, m), prior diag(tilde_tau(j,m) * gamma(j,.,m))
@@ -888,7 +914,7 @@ int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtY
     }
   }
   s->pre_next = -1;
-  return rc;
+  return rc ? rc : tape_check(s);
 }
 // updateNu (UpdateNu.h:24-74): blocks j, prior tau_j * P (MV: (1/tau_j) I, :195-196)
 int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
@@ -928,7 +954,7 @@ int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW
     }
   }
   s->pre_next = -1;
-  return rc;
+  return rc ? rc : tape_check(s);
 }
 // updateEta (UpdateEta.h:28-94): d outer, j inner; prior tau_eta(j,d) * P (MV: (1/tau_eta) I)
 int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
@@ -947,7 +973,7 @@ int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtY
         if (block_draw(s, j, 0, d + 1, WtW, BtYW, beta, prior.data(), nullptr)) return 1;
       }
     }
-  return 0;
+  return tape_check(s);
 }
 // updateXiCovariateAdj (UpdateXi.h:26-93): order j, m, d; prior diag(tilde_tau_xi(j,m,d) * gamma_xi_j(.,d,m))
 int bfmmm_host_update_xi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
@@ -962,7 +988,7 @@ int bfmmm_host_update_xi(bfmmm_sampler* s, const double* WtW, const double* BtYW
         for (int p = 0; p < P; p++) diag[p] = tt * s->gamma_xi_(j, p, d, m);
         if (block_draw(s, j, m + 1, d + 1, WtW, BtYW, beta, nullptr, diag.data())) return 1;
       }
-  return 0;
+  return tape_check(s);
 }
 
 // updateSigma's draw (UpdateSigma.h:47-53; tempered :98-107; MV :149-151)
@@ -973,7 +999,7 @@ int bfmmm_host_update_sigma(bfmmm_sampler* s, double ssr, double beta, int tempe
   else { a = s->sum_half_total + s->h.alpha_0; b1 = 0.5 * ssr + s->h.beta_0; }
   double r = (1 / b1) * s->rng.gamma(a);
   s->sigma_sq = 1 / r;
-  return 0;
+  return tape_check(s);
 }
 
 // ================================================================= stored samples
@@ -1056,6 +1082,7 @@ int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   const double t0 = now_s(), w0 = s->t_wait, p0 = s->t_push;
   int rc = sampler_step_impl(s, sweep, beta);
   s->t_host += (now_s() - t0) - (s->t_wait - w0) - (s->t_push - p0);
+  if (s->rng.tape_underrun) { s->rng.tape_underrun = false; if (!rc) rc = sfail("bfmmm_sampler_step: the tape of injected draws ran out during the sweep"); }
   return rc;
 }
 // seconds spent so far in: host-side draws | waiting on the device | pushing globals
@@ -1071,7 +1098,9 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   const bool do_phi = (sweep == BFMMM_SWEEP_THETA || sweep == BFMMM_SWEEP_FULL);
   const bool do_nu = do_z;
   const bool do_chi = do_phi;
-  const bool tempered = beta != 1.0;
+  // updateSigmaTempered's shape a = sum_i beta n_i / 2 (real division, UpdateSigma.h:98-107) is used on EVERY rung of a
+  // tempered transition, the beta = 1 rungs included (BFMMM.h:1556-1651); updateSigma's sum_i floor(n_i / 2) otherwise
+  const bool tempered = s->in_tt || beta != 1.0;
   if (bfmmm_seed(e, s->rng.key, (uint64_t)s->tick)) return 1;
   if (push_globals(s)) return 1;
   if (do_z) {                                              // updateZ_PM -> updatePi_PM -> updateAlpha3
@@ -1209,12 +1238,18 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
   if (reduce_and_read(s, /*only_ssr=*/true)) return 1;
   s->tt_ssr.assign(m + 1, 0.0); s->tt_sigma.assign(m + 1, 0.0);
   s->tt_ssr[0] = st_ssr(s); s->tt_sigma[0] = s->sigma_sq;
-  bfmmm_sampler saved = *s;                       // host-side copy of every global
+  const ChainParams saved = save_params(s);       // the chain's globals only (not the recorder's kept draws or scratch)
   if (bfmmm_state_snapshot(s->e)) return 1;
   int temp_ind = 0;
   s->in_tt = true;
   for (int l = 1; l <= m; l++) {
-    if (bfmmm_sampler_step(s, BFMMM_SWEEP_FULL, ladder[temp_ind])) { s->in_tt = false; return 1; }
+    if (bfmmm_sampler_step(s, BFMMM_SWEEP_FULL, ladder[temp_ind])) {
+      // a failed rung leaves nothing half-advanced: globals and (Z, chi) go back to the pre-transition state
+      s->in_tt = false;
+      restore_params(s, saved);
+      bfmmm_state_restore(s->e);
+      return 1;
+    }
     s->tt_ssr[l] = s->last_ssr; s->tt_sigma[l] = s->sigma_sq;
     if (l < N_t) temp_ind++;
     if (l > N_t) temp_ind--;
@@ -1236,13 +1271,8 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
   s->tt_total++;
   if (ok) s->tt_accepts++;
   else {
-    // restore the pre-transition state but keep the bookkeeping that must advance
-    vecd tssr = s->tt_ssr, tsig = s->tt_sigma;
-    int64_t tk = s->tick, acc = s->tt_accepts, tot = s->tt_total;
-    HostRng rng = s->rng;
-    *s = saved;
-    s->tt_ssr = tssr; s->tt_sigma = tsig; s->tick = tk; s->tt_accepts = acc; s->tt_total = tot; s->rng = rng;
-    if (s->ragged) s->Hb = st_hb(s);
+    // restore the pre-transition parameters; the bookkeeping (tick, counters, traces, random streams) moves on
+    restore_params(s, saved);
     if (bfmmm_state_restore(s->e)) return 1;
   }
   if (s->rec.on && record_iteration(s)) return 1;

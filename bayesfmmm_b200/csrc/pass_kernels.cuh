@@ -4,7 +4,8 @@
 // warp reads 512 contiguous bytes per row.  The global coefficients live in shared memory
 // (broadcast reads).  K and M are compile-time so all per-function state stays in registers.
 #pragma once
-#include <unordered_map>
+#include <map>
+#include <mutex>
 #include <utility>
 
 #include "common.cuh"
@@ -198,8 +199,8 @@ __device__ __forceinline__ void stage_globals(const PassArgs& a, double* g) {
 // Z_proposal_density :102-113; rdirichlet Distributions.h:22-45; calc_lB :51-61).
 // The squared-error terms are evaluated in the whitened coefficient space, where
 // ||y - B theta||^2 = rss_i + ||c~_i - theta~||^2 and rss_i cancels in the ratio.
-// log Z of the current state is read from the cache a.lZ (and written back with Z), every other
-// transcendental goes through fastmath.cuh.
+// No logarithm of a membership and no log-Gamma is evaluated on the common path (closed forms below);
+// the remaining transcendentals go through fastmath.cuh.
 
 // Rows of the coefficient cache in groups of four, two groups alternating (A is consumed while B is in
 // flight and vice versa: no register copies).  begin() issues the first group, so the caller can put
@@ -235,29 +236,127 @@ struct RowStream {
   }
 };
 
-// generic proposal sampler (rejected fast-path candidate, or K > 4): out of line, rarely executed
+// Generic proposal (K > 4, or a membership that is not positive: the reference's rdirichlet replaces its
+// concentration by 10, Distributions.h:24-28): the general gamma sampler on its own stream.  Out of line, rare.
 template <int K>
-__device__ __noinline__ void z_slow_proposal(uint64_t key, uint64_t gi, uint64_t iteration, const double* sh, double* zp,
+__device__ __noinline__ void z_slow_proposal(uint64_t key, uint64_t gi, uint64_t iteration, const double* z, double a_Z, double* zp,
                                              double* uacc, bool live) {
   RngStream rs(key, gi, iteration, RNG_Z_PROPOSAL_SLOW);
 #pragma unroll
-  for (int k = 0; k < K; k++) zp[k] = live ? rs.gamma(sh[k]) : 1.0;
+  for (int k = 0; k < K; k++) {
+    double sh = a_Z * z[k];
+    if (!(sh > 0)) sh = 10;                                              // Distributions.h:24-28
+    zp[k] = live ? rs.gamma(sh) : 1.0;
+  }
   if (K > 4) *uacc = rs.uniform();
 }
-static __device__ __noinline__ double nl_pow_u(double u, double inv_shape) { return exp(log(u) * inv_shape); }
 
-// log Gamma(tot) for tot = a * sum_k z_k, which equals a up to rounding when the row of Z sums to one:
-// second-order Taylor series around a (error |dt|^3 / (6 a^2)), the general routine otherwise
-__device__ __forceinline__ double lgamma_near_a(double tot, const PassArgs& a) {
-  const double dt = tot - a.a_Z_PM;
-  if (fabs(dt) <= 1e-8 * a.a_Z_PM) return fma(dt, fma(0.5 * dt, a.trigam_a, a.digam_a), a.lgam_a);
-  return lgamma_shift16(tot, fast_log_nl(tot));     // rows of Z that do not sum to one (rare): the shift is valid for any tot > 0
+// The Metropolis log-ratio without the likelihood term, written out as the reference does
+// (UpdateMixedMembership.h:33-36,102-113,165-168; Distributions.h:51-61):
+//   sum_k (alpha_3 pi_k - 1)(log z*_k - log z_k) + q(z | a z*) - q(z* | a z),
+//   q(x | al) = sum_k (al_k - 1) log x_k - [sum_k lgamma(al_k) - lgamma(sum_k al_k)].
+// Out of line: only functions outside the domain of the closed form below come here (a membership that is not
+// positive, a proposal coordinate that underflowed to zero, rows of Z that do not sum to one).
+template <int K>
+__device__ __noinline__ double z_logratio_exact(const double* z, const double* zp, const double* pi, double alpha3, double a) {
+  double lp = 0, q_new = 0, q_old = 0, lB_new = 0, lB_old = 0, tot_new = 0, tot_old = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const double lz = log(z[k]), lzp = log(zp[k]);
+    const double al_from_old = a * z[k], al_from_new = a * zp[k];
+    lp = fma(alpha3 * pi[k] - 1, lzp - lz, lp);
+    q_new = fma(al_from_old - 1, lzp, q_new);
+    q_old = fma(al_from_new - 1, lz, q_old);
+    lB_new += lgamma(al_from_old); tot_new += al_from_old;
+    lB_old += lgamma(al_from_new); tot_old += al_from_new;
+  }
+  q_new -= (lB_new - lgamma(tot_new));
+  q_old -= (lB_old - lgamma(tot_old));
+  return lp + (q_old - q_new);
+}
+
+// S(1/x) = lgamma(x) - [(x - 1/2) log x - x + log(2 pi)/2] for any x > 0 below 16, where Stirling's series is not
+// accurate: through the shift Gamma(x) = Gamma(x + 16) / (x ... (x + 15)).  S(1/xp) - S(1/x) for a coordinate whose
+// current or proposed concentration is below 16 (a membership below 16 / a): out of line, one call per such coordinate.
+static __device__ __noinline__ double stirling_corr_diff_small(double x, double rx, double xp, double rxp) {
+  double so = stirling_corr(rx), sn = stirling_corr(rxp);
+  if (x < 16.0) { const double lx = fast_log(x); so = lgamma_shift16(x, lx) - (fma(x - 0.5, lx, -x) + 0.918938533204672741780329736406); }
+  if (xp < 16.0) { const double lx = fast_log(xp); sn = lgamma_shift16(xp, lx) - (fma(xp - 0.5, lx, -xp) + 0.918938533204672741780329736406); }
+  return sn - so;
 }
 
 #ifndef BF_Z_MINB
-#define BF_Z_MINB 5       // resident blocks per SM the register allocation of the V = 1 common-grid Z kernel targets
-                          // (96 registers; measured 8: 122 us, 7: 119, 6: 116, 5: 109, 4: 114 -- spills cost more than warps)
+#define BF_Z_MINB 6       // resident blocks per SM the register allocation of the V = 1 common-grid Z kernel targets
 #endif
+// The log-ratio in closed form.  With sh_k = a z_k, sh*_k = a z*_k, dl_k = log z*_k - log z_k and Stirling's
+// lgamma(x) = (x - 1/2) log x - x + log(2 pi)/2 + S(1/x), every log-Gamma main term folds into the log terms:
+//   q(z | a z*) - q(z* | a z) = - sum_k (sh_k + sh*_k - 3/2) dl_k - sum_k [S(1/sh*_k) - S(1/sh_k)]
+//                               + (1 - log a)(tot* - tot) + lgamma(tot*) - lgamma(tot),     tot = sum_k sh_k,
+// so no log-Gamma is evaluated and the only logarithm per coordinate is the one of the ratio z*_k / z_k: the summands
+// are O(a |dl|) instead of the O(a log a) of the 2(K + 1) log-Gammas the reference sums (its own rounding error,
+// 2(K+1) ulp(lgamma(a)) ~ 1e-10 at a = 1e4, is what bounds the parity of this quantity; see tests/test_gpu_parity.py).
+// The identity holds for every positive z, z*; S itself is Stirling's series above 16 and the shifted form below.
+// lgamma(tot*) - lgamma(tot) is the second-order Taylor expansion around a (rows of Z sum to one up to rounding;
+// `ok` is cleared otherwise and the caller evaluates the reference's formula as written).
+template <int K>
+__device__ __forceinline__ double z_logratio_closed(const double (&sh)[K], const double (&r)[K], const double (&zp)[K],
+                                                    const double (&dl)[K], const PassArgs& a, bool& ok) {
+  double acc = 0, tot = 0, tots = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const double shp = a.a_Z_PM * zp[k];
+    const double rp = fast_rcp1(shp);
+    acc = fma(fma(a.alpha3, a.pi[k], 0.5) - (sh[k] + shp), dl[k], acc);
+    double ds = stirling_corr(rp) - stirling_corr(r[k]);
+    if (shp < 16.0 || sh[k] < 16.0) ds = stirling_corr_diff_small(sh[k], r[k], shp, rp);
+    acc -= ds;
+    tot += sh[k]; tots += shp;
+  }
+  const double dt = tot - a.a_Z_PM, dts = tots - a.a_Z_PM;
+  ok = ok && (fabs(dt) <= 1e-8 * a.a_Z_PM) && (fabs(dts) <= 1e-8 * a.a_Z_PM);
+  acc = fma(dts - dt, a.c_tot, acc);                       // c_tot = 1 - log a + digamma(a)
+  return fma(0.5 * a.trigam_a, (dts - dt) * (dts + dt), acc);
+}
+
+// One round of Marsaglia-Tsang candidates for the coordinates still pending (bit k of `pend`): three Philox blocks
+// give two Box-Muller pairs (4 normals) and four 32-bit accept uniforms.  Candidate g = d v, d = s - 1/3,
+// v = (1 + c x)^3 with s = sh (sh >= 1) or sh + 1 (boosted below); accepted when log uu < x^2/2 + d (1 - v + log v),
+// decided without a logarithm when uu - 1 < R (log uu <= uu - 1).  Coordinates are independent rejection samplers, so
+// a rejected one simply draws again in the next round (blocks 3 r .. 3 r + 2); at the default a_Z_PM a round rejects
+// ~1e-5 of the candidates, ~5e-2 of those with sh < 2.
+template <int K>
+__device__ __forceinline__ unsigned z_candidate_round(const PassArgs& a, uint64_t gi, uint32_t block0, const double (&sh)[K],
+                                                      unsigned pend, double (&g)[K], double& uacc, bool first) {
+  uint32_t w0[4], w1[4], w2[4];
+  philox_rk(a, gi, RNG_Z_PROPOSAL, block0, w0);
+  philox_rk(a, gi, RNG_Z_PROPOSAL, block0 + 1, w1);
+  philox_rk(a, gi, RNG_Z_PROPOSAL, block0 + 2, w2);
+  double nrm[4] = {0, 0, 0, 0}, ua[4];
+  fast_box_muller(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
+  if constexpr (K > 2) fast_box_muller(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
+  ua[0] = u32(w0[3]); ua[1] = u32(w1[3]); ua[2] = u32(w2[2]); ua[3] = u32(w2[3]);
+  if (first) uacc = u52(w2[0], w2[1]);
+  unsigned left = pend;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const double d = (sh[k] < 1.0 ? sh[k] + 1.0 : sh[k]) - 1.0 / 3.0;
+    const double c = fast_rsqrt_seed1(9.0 * d);
+    const double t = c * nrm[k];
+    const double v1 = 1.0 + t;
+    const double vv = v1 * v1 * v1;
+    const bool in = t > -0.99;
+    const double l3 = 3.0 * fast_log_pos(in ? v1 : 1.0);
+    const double R = fma(0.5 * nrm[k], nrm[k], d * (1.0 - vv + l3));
+    if (((pend >> k) & 1u) != 0) {
+      g[k] = d * vv;
+      bool ok = in && (ua[k] - 1.0 < R);
+      if (in && !ok) ok = fast_log_nl(ua[k]) < R;      // the exact test, for the few candidates the squeeze did not decide
+      if (ok) left &= ~(1u << k);
+    }
+  }
+  return left;
+}
+
 template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
@@ -273,103 +372,103 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
     st.load(a, i0);
     RowStream<V> rows;
     if constexpr (!RG) rows.begin(a.Ct + i0, a.ld);      // first rows in flight during the proposal
-    double zp[V][K], uacc[V], lzo[V][K], lzn[V][K];
-    {
-      double t[V];
+    // Everything that does not need the coefficient cache comes first -- the proposal z*, the Metropolis uniform and
+    // the log-ratio lr of prior and proposal densities -- so that only z, z*, chi, lr and log u are live across the
+    // row loop (the loop's own state is what sets the register count, not the transcendental code).
+    double zp[V][K], lr[V], lu[V];
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        ldv<V>(a.lZ + (size_t)k * a.ld + i0, t);
-#pragma unroll
-        for (int v = 0; v < V; v++) lzo[v][k] = t[v];
-      }
-    }
-    // ---- proposal
-    if (a.gam) {
-      double t[V];
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        ldv_cs<V>(a.gam + (size_t)k * a.ld + i0, t);
-#pragma unroll
-        for (int v = 0; v < V; v++) zp[v][k] = t[v];
-      }
-      ldv_cs<V>(a.u + i0, uacc);
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        double sum = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++) sum += zp[v][k];
-#pragma unroll
-        for (int k = 0; k < K; k++) { zp[v][k] = zp[v][k] / sum; lzn[v][k] = fast_log(zp[v][k]); }
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
-        const bool live = (i0 + v) < a.n;
-        bool fast = (K <= 4);
-        // The random words and the normals do not depend on the state: they are generated first, so the
-        // loads of Z, chi and log Z issued above are in flight for a few hundred instructions before their
-        // first use (they were 11 % of the kernel's stall samples when the shapes were computed first).
-        // Straight-line path: three Philox blocks give two Box-Muller pairs (4 normals), four 32-bit
-        // accept uniforms and the Metropolis uniform; one Marsaglia-Tsang candidate per coordinate.
-        double nrm[4] = {0, 0, 0, 0}, ua[4] = {0.5, 0.5, 0.5, 0.5};
-        if constexpr (K <= 4) {
-          uint32_t w0[4], w1[4], w2[4];
-          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 0, w0);
-          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 1, w1);
-          philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 2, w2);
-          fast_box_muller(w0[0], w0[1], w0[2], nrm[0], nrm[1]);
-          if constexpr (K > 2) fast_box_muller(w1[0], w1[1], w1[2], nrm[2], nrm[3]);
-          ua[0] = u32(w0[3]); ua[1] = u32(w1[3]); ua[2] = u32(w2[2]); ua[3] = u32(w2[3]);
-          uacc[v] = u52(w2[0], w2[1]);
-        }
-        bool small = false;
-        double sh[K];
+    for (int v = 0; v < V; v++) {
+      const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
+      const bool live = (i0 + v) < a.n;
+      double sh[K], rr[K], dl[K], uacc = 0.5, sum = 0;
+      bool generic = (K > 4);        // the gamma variates must come from the generic sampler
+      bool pos = true;               // every membership is positive (and normal): the closed forms apply
+      if (a.gam) {                   // injected draws (parity)
 #pragma unroll
         for (int k = 0; k < K; k++) {
           sh[k] = a.a_Z_PM * st.z[v][k];
-          if (!(sh[k] > 0)) sh[k] = 10;                                   // Distributions.h:24-28
+          pos = pos && (sh[k] > 1e-290);
+          zp[v][k] = __ldcs(a.gam + (size_t)k * a.ld + i0 + v); sum += zp[v][k];
+        }
+        uacc = __ldcs(a.u + i0 + v);
+        generic = false;
+      } else if constexpr (K <= 4) {
+        // the first round's random words and normals do not depend on the state: the loads issued above are in
+        // flight while they are made
+        double gk[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) sh[k] = 1.0;
+        unsigned pend = (1u << K) - 1u;
+        // (sh is filled in below, after the words of round 0 are under way: z_candidate_round reads it late)
+        bool small = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          sh[k] = a.a_Z_PM * (live ? st.z[v][k] : 1.0 / K);
+          pos = pos && (sh[k] > 1e-290);                                  // false for NaN and z <= 0 too
           small = small || (sh[k] < 1.0);
         }
-        if constexpr (K <= 4) {
-          // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are
-          // only generated by warps that contain such a function
-          double ub[4] = {0.5, 0.5, 0.5, 0.5};
-          if (__any_sync(__activemask(), small)) {
-            uint32_t w3[4], w4[4];
-            philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 3, w3);
-            philox_words(a.key, gi, a.iteration, RNG_Z_PROPOSAL, 4, w4);
-            ub[0] = u53(w3[0], w3[1]); ub[1] = u53(w3[2], w3[3]); ub[2] = u53(w4[0], w4[1]); ub[3] = u53(w4[2], w4[3]);
-          }
+        generic = !pos;
+        pend = z_candidate_round<K>(a, gi, 0, sh, pend, gk, uacc, true);
+        for (uint32_t round = 1; round < 24 && __any_sync(__activemask(), pend != 0); round++)
+          pend = z_candidate_round<K>(a, gi, 8 + 3 * round, sh, pend, gk, uacc, false);
+        generic = generic || (pend != 0);
+        // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are only generated by
+        // warps that contain such a function
+        if (__any_sync(__activemask(), small)) {
+          uint32_t w3[4], w4[4];
+          philox_rk(a, gi, RNG_Z_PROPOSAL, 3, w3);
+          philox_rk(a, gi, RNG_Z_PROPOSAL, 4, w4);
+          const double ub[4] = {u52(w3[0], w3[1]), u52(w3[2], w3[3]), u52(w4[0], w4[1]), u52(w4[2], w4[3])};
 #pragma unroll
-          for (int k = 0; k < K; k++) {
-            const bool bo = sh[k] < 1.0;
-            const bool ok = gamma_candidate_fast(bo ? sh[k] + 1.0 : sh[k], nrm[k], ua[k], zp[v][k]);
-            if (bo) zp[v][k] *= nl_pow_u(ub[k], 1.0 / sh[k]);
-            fast = fast && ok;
-          }
+          for (int k = 0; k < K; k++)
+            if (sh[k] < 1.0) gk[k] *= fast_exp_nonpos(fast_log_pos(ub[k]) * fast_rcp(pos ? sh[k] : 1.0));
         }
-        if (!fast) {          // a rejected candidate or K > 4: generic sampler on its own stream
-          double tsh[K], tzp[K], tu = uacc[v];     // only these copies have their address taken
 #pragma unroll
-          for (int k = 0; k < K; k++) tsh[k] = sh[k];
-          z_slow_proposal<K>(a.key, gi, a.iteration, tsh, tzp, &tu, live);
+        for (int k = 0; k < K; k++) { zp[v][k] = gk[k]; sum += gk[k]; }
+      } else {
 #pragma unroll
-          for (int k = 0; k < K; k++) zp[v][k] = tzp[k];
-          uacc[v] = tu;
-        }
-        double sum = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++) sum += zp[v][k];
-        if (a.draws_out) {
-#pragma unroll
-          for (int k = 0; k < K; k++) a.draws_out[(size_t)k * a.ld + i0 + v] = zp[v][k];
-          a.draws_out[(size_t)K * a.ld + i0 + v] = uacc[v];
-        }
-        const double rs = (sum > 1e-290 && sum < 1e290) ? fast_rcp(sum) : 1.0 / sum;
-#pragma unroll
-        for (int k = 0; k < K; k++) { zp[v][k] *= rs; lzn[v][k] = fast_log(zp[v][k]); }
+        for (int k = 0; k < K; k++) { sh[k] = a.a_Z_PM * st.z[v][k]; pos = pos && (sh[k] > 1e-290); }
       }
+      if (generic) {
+        double tz[K], tzp[K], tu = uacc;     // only these copies have their address taken
+#pragma unroll
+        for (int k = 0; k < K; k++) tz[k] = st.z[v][k];
+        z_slow_proposal<K>(a.key, gi, a.iteration, tz, a.a_Z_PM, tzp, &tu, live);
+        sum = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) { zp[v][k] = tzp[k]; sum += tzp[k]; }
+        uacc = tu;
+      }
+      if (a.draws_out) {
+#pragma unroll
+        for (int k = 0; k < K; k++) a.draws_out[(size_t)k * a.ld + i0 + v] = zp[v][k];
+        a.draws_out[(size_t)K * a.ld + i0 + v] = uacc;
+      }
+      if (a.gam || generic) {          // the reference's division (Distributions.h:39-43): same bits as the oracle
+#pragma unroll
+        for (int k = 0; k < K; k++) zp[v][k] = zp[v][k] / sum;
+      } else {                         // straight-line path: the sum of K positive normal numbers
+        const double rs = fast_rcp(sum);
+#pragma unroll
+        for (int k = 0; k < K; k++) zp[v][k] *= rs;
+      }
+      // ---- log-ratio of prior and proposal densities
+      bool closed = pos;
+#pragma unroll
+      for (int k = 0; k < K; k++) closed = closed && (zp[v][k] > 1e-290);
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        rr[k] = fast_rcp(closed ? sh[k] : 1.0);
+        dl[k] = fast_log_pos(closed ? zp[v][k] * (a.a_Z_PM * rr[k]) : 1.0);      // log(z*_k / z_k)
+      }
+      lr[v] = z_logratio_closed<K>(sh, rr, zp[v], dl, a, closed);
+      if (!closed) {
+        double tz[K], tzp[K], tpi[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) { tz[k] = st.z[v][k]; tzp[k] = zp[v][k]; tpi[k] = a.pi[k]; }
+        lr[v] = z_logratio_exact<K>(tz, tzp, tpi, a.alpha3, a.a_Z_PM);
+      }
+      lu[v] = fast_log(uacc);
     }
     // ---- squared errors of the current and the proposed state
     double so[V], sn[V];
@@ -425,40 +524,21 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
       });
     }
     // ---- acceptance
-    double znew[V][K], lznew[V][K];
+    double znew[V][K];
 #pragma unroll
     for (int v = 0; v < V; v++) {
-      double lp = 0;                 // lpdf(z*) - lpdf(z)
       bool nonpos = false;
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        lp = fma(a.alpha3 * a.pi[k] - 1, lzn[v][k] - lzo[v][k], lp);
-        nonpos |= (st.z[v][k] <= 0);
-      }
-      lp = fma(-hb, sn[v] - so[v], lp);
-      double q_new = 0, q_old = 0, lB_new = 0, lB_old = 0, tot_new = 0, tot_old = 0;
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        const double al_from_old = a.a_Z_PM * st.z[v][k];   // parameters used to propose the new state
-        const double al_from_new = a.a_Z_PM * zp[v][k];     // parameters of the reverse move
-        q_new = fma(al_from_old - 1, lzn[v][k], q_new);
-        q_old = fma(al_from_new - 1, lzo[v][k], q_old);
-        // log(a * z) = log a + log z: both logs are already in registers
-        lB_new += lgamma_pos(al_from_old, a.log_a_Z_PM + lzo[v][k]); tot_new += al_from_old;
-        lB_old += lgamma_pos(al_from_new, a.log_a_Z_PM + lzn[v][k]); tot_old += al_from_new;
-      }
-      q_new -= (lB_new - lgamma_near_a(tot_new, a));
-      q_old -= (lB_old - lgamma_near_a(tot_old, a));
-      double acc = lp + (q_old - q_new);
+      for (int k = 0; k < K; k++) nonpos |= (st.z[v][k] <= 0);
+      double acc = fma(-hb, sn[v] - so[v], lr[v]);
       if (nonpos) acc = 1;                           // UpdateMixedMembership.h:170-174
       const bool live = (i0 + v) < a.n;
-      const bool take = live && (fast_log(uacc[v]) < acc);
+      const bool take = live && (lu[v] < acc);
       if (a.acc_out && live) a.acc_out[i0 + v] = acc;
 #pragma unroll
       for (int k = 0; k < K; k++) {
         znew[v][k] = take ? zp[v][k] : st.z[v][k];
-        lznew[v][k] = take ? lzn[v][k] : lzo[v][k];
-        if (live) red[k] += lznew[v][k];
+        if (live) red[k] += fast_log(znew[v][k]);    // sum_i log Z_ik of the new state: updatePi_PM / updateAlpha3's statistic
       }
       if (take) red[K] += 1.0;
     }
@@ -469,9 +549,6 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
 #pragma unroll
         for (int v = 0; v < V; v++) t[v] = znew[v][k];
         stv<V>(a.Z + (size_t)k * a.ld + i0, t);
-#pragma unroll
-        for (int v = 0; v < V; v++) t[v] = lznew[v][k];
-        stv<V>(a.lZ + (size_t)k * a.ld + i0, t);
       }
     }
   }
@@ -501,6 +578,32 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
   extern __shared__ double g[];
   build_log_table();
   stage_globals(a, g);
+  // Common basis without covariates: u_m = sum_k z_k phi~_km, so the per-function Gram is a quadratic form in z,
+  //   G_i[m][n] = u_m . u_n = sum_{k <= k'} z_k z_k' Q[mn][kk'],   Q[mn][kk'] = phi~_km . phi~_k'n (+ phi~_k'm . phi~_kn, k != k'),
+  // with Q a property of the globals only: the block builds it once, and the row loop keeps just the data-dependent
+  // part (the residual d = c~ - mu~ and s[k][m] = phi~_km . d, from which r[m] = sum_k z_k s[k][m]): 4 + K M
+  // multiply-adds per row instead of 1 + K + K M + M + M(M+1)/2.
+  constexpr bool GQ = !COV && !RG;
+  constexpr int NKK = K * (K + 1) / 2, NMN = M * (M + 1) / 2;
+  __shared__ __align__(16) double Qs[GQ ? NMN * NKK : 1];
+  if constexpr (GQ) {
+    for (int idx = threadIdx.x; idx < NMN * NKK; idx += blockDim.x) {
+      int mn = idx / NKK, kk = idx % NKK, m = 0, n = 0, k = 0, k2 = 0;
+      for (int t = mn; t >= M - m; t -= M - m, m++) {}
+      { int t = mn; for (int j = 0; j < m; j++) t -= M - j; n = m + t; }
+      for (int t = kk; t >= K - k; t -= K - k, k++) {}
+      { int t = kk; for (int j = 0; j < k; j++) t -= K - j; k2 = k + t; }
+      const int f1 = k * (M + 1) + m + 1, f2 = k2 * (M + 1) + n + 1, f3 = k2 * (M + 1) + m + 1, f4 = k * (M + 1) + n + 1;
+      double q1 = 0, q2 = 0;
+      for (int p = 0; p < a.P4; p++) {
+        const double* gp = g + p * a.QS;
+        q1 = fma(gp[f1], gp[f2], q1);
+        q2 = fma(gp[f3], gp[f4], q2);
+      }
+      Qs[idx] = (k == k2) ? q1 : q1 + q2;
+    }
+    __syncthreads();
+  }
   double red[1] = {0};
   const double bs = a.beta / (a.sigma_dev ? *a.sigma_dev : a.sigma_sq);
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
@@ -518,7 +621,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
 #pragma unroll
         for (int pr = 0; pr < (M + 1) / 2; pr++) {
           uint32_t w[4];
-          philox_words(a.key, gi, a.iteration, RNG_CHI, pr, w);
+          philox_rk(a, gi, RNG_CHI, pr, w);
           double n0, n1;
           fast_box_muller(w[0], w[1], w[2], n0, n1);
           eps[v][2 * pr] = n0;
@@ -537,6 +640,55 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
         for (int q = 0; q < M; q++) G[v][m][q] = 0;
       }
     }
+    if constexpr (GQ) {
+      double sk[V][K][M];
+#pragma unroll
+      for (int v = 0; v < V; v++)
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+          for (int m = 0; m < M; m++) sk[v][k][m] = 0;
+      constexpr int QSc = (K * (M + 1) + 1) & ~1;
+      Coef<K, M, false, V> cf;
+      rows.run(a.P4, [&](int p, const double (&c)[V]) {
+        cf.load(g + p * QSc, 0, st.x);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          double dres = c[v];
+#pragma unroll
+          for (int k = 0; k < K; k++) dres = fma(-st.z[v][k], cf.get(v, k, 0), dres);
+          d0[v] = fma(dres, dres, d0[v]);
+#pragma unroll
+          for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int m = 0; m < M; m++) sk[v][k][m] = fma(cf.get(v, k, m + 1), dres, sk[v][k][m]);
+        }
+      });
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        double zz[NKK];
+        {
+          int t = 0;
+#pragma unroll
+          for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int k2 = k; k2 < K; k2++, t++) zz[t] = st.z[v][k] * st.z[v][k2];
+        }
+        int mn = 0;
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+#pragma unroll
+          for (int k = 0; k < K; k++) r[v][m] = fma(st.z[v][k], sk[v][k][m], r[v][m]);
+#pragma unroll
+          for (int q = m; q < M; q++, mn++) {
+            double t = 0;
+#pragma unroll
+            for (int kk = 0; kk < NKK; kk++) t = fma(Qs[mn * NKK + kk], zz[kk], t);
+            G[v][m][q] = t;
+          }
+        }
+      }
+    } else {
     Coef<K, M, COV, V> cf;
     constexpr int NB = RG ? BWMAX : 0;
     BandWin wd[V], wu[V][M];
@@ -590,6 +742,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
     } else {
       const double nogb[1][V] = {};
       rows.run(a.P4, [&](int p, const double (&c)[V]) { body(p, c, nogb); });
+    }
     }
     if constexpr (CPO) {
       double rssv[V];
@@ -767,22 +920,29 @@ template <int V, typename Kern>
 inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extra_smem = 0) {
   size_t smem = (size_t)a.P4 * a.QS * sizeof(double) + extra_smem;
   // resident blocks per SM of this instantiation (queried once), grid = one full wave
-  static std::unordered_map<const void*, std::pair<size_t, int>> cache;   // kernel -> (smem, blocks per SM)
+  // (kernel, device) -> (smem, blocks per SM): the attribute and the occupancy are per device; several host threads
+  // may drive several engines (one per GPU), so the cache is locked
+  static std::map<std::pair<const void*, int>, std::pair<size_t, int>> cache;
+  static std::mutex cache_mu;
   int dev = 0;
   cudaGetDevice(&dev);
-  const void* key = (const void*)((const char*)kern + dev);      // the attribute / occupancy are per device
-  auto it = cache.find(key);
-  if (it == cache.end() || it->second.first != smem) {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
+  int per_sm = 0;
+  {
+    std::lock_guard<std::mutex> lock(cache_mu);
+    const auto key = std::make_pair((const void*)kern, dev);
+    auto it = cache.find(key);
+    if (it == cache.end() || it->second.first != smem) {
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+      }
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PF_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+      cache[key] = std::make_pair(smem, nb);
+      it = cache.find(key);
     }
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PF_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
-    cache[key] = std::make_pair(smem, nb);
-    it = cache.find(key);
+    per_sm = it->second.second;
   }
-  const int per_sm = it->second.second;
   int need = pass_grid(a.ld, V);
   int grid = a.sm_count * per_sm;
   if (grid > need) grid = need;

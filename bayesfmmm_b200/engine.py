@@ -202,6 +202,12 @@ class Engine:
         self._chk(self._lib.bfmmm_engine_dims(self._h, d))
         return tuple(int(x) for x in d)
 
+    def counts(self):
+        """(sum_i floor(n_i / 2), sum_i n_i) of this shard (UpdateSigma.h:49, CalculateLikelihood.h:40)"""
+        a, b = C.c_double(), C.c_double()
+        self._chk(self._lib.bfmmm_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def gram(self):
         G = np.zeros((self.P, self.P), order="F")
         self._chk(self._lib.bfmmm_get_gram(self._h, _p(G)))

@@ -110,7 +110,7 @@ int bfmmm_state_snapshot(bfmmm_engine* e);
 int bfmmm_state_restore(bfmmm_engine* e);
 
 /* ---- global parameters: pushed before the phases that read them ----------------------------- */
-/* eta/xi may be NULL when D == 0; Phi may be NULL when M == 0. */
+/* eta/xi may be NULL when D == 0 (M >= 1 always: bfmmm_create rejects M < 1). */
 int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, const double* eta,
                       const double* xi, double sigma_sq);
 

@@ -86,6 +86,9 @@ int bfmmm_sampler_set_counts(bfmmm_sampler* s, double sum_half_total, double n_p
 int bfmmm_sampler_set(bfmmm_sampler* s, const double* nu, const double* Phi, const double* sigma_sq,
                       const double* pi, const double* alpha3, const double* delta, const double* gamma,
                       const double* A, const double* tau);
+/* NOTE (multi-GPU): with an all-reduce hook installed, asking for `loglik` completes the deferred post-chi SSR
+ * exchange, i.e. bfmmm_sampler_get(..., loglik != NULL) is a COLLECTIVE: call it on every rank or on none.
+ * With loglik == NULL the call is rank-local. */
 int bfmmm_sampler_get(bfmmm_sampler* s, double* nu, double* Phi, double* sigma_sq, double* pi,
                       double* alpha3, double* delta, double* gamma, double* A, double* tau, double* loglik);
 int bfmmm_sampler_set_cov(bfmmm_sampler* s, const double* eta, const double* xi, const double* tau_eta,

@@ -260,6 +260,7 @@ struct BlockEngine {
     std::fill(m1.begin(), m1.end(), 0.0);
     std::vector<Block> bs = all_blocks();
     std::vector<double> theta(P);
+    std::vector<int> nz;
     for (int i = 0; i < n; i++) {
       if (v.Z(i, tgt.k) == 0) continue;
       double wa = weight(tgt, i);
@@ -285,10 +286,13 @@ struct BlockEngine {
         for (int p = 0; p < P; p++) mean += theta[p] * b[p];
         double ph = v.y(i, l) - mean;
         double s2 = wa * wa;
-        for (int c = 0; c < P; c++) {
-          if (b[c] == 0.0) continue;
+        // outer product B_l B_l' restricted to the non-zero basis values of this point (the skipped
+        // terms are exact zeros: a tensor-product cubic basis has 16 of P = 400)
+        nz.clear();
+        for (int c = 0; c < P; c++) if (b[c] != 0.0) nz.push_back(c);
+        for (int c : nz) {
           double sc = s2 * b[c];
-          for (int r = 0; r < P; r++) M1[(size_t)c * P + r] += sc * b[r];
+          for (int r : nz) M1[(size_t)c * P + r] += sc * b[r];
         }
         double wp = wa * ph;
         for (int p = 0; p < P; p++) m1[p] += wp * b[p];

@@ -17,13 +17,32 @@ CASES = {
     # P >= 96: the host block draws factorise the (banded) precisions on several threads before drawing
     "F_common_P100": ("common", dict(seed=18, n=40, T=130, K=2, P=100, M=2)),
     "MV_R100": ("mv", dict(seed=19, n=40, R=100, K=2, M=2)),
+    # BASELINE.json's own shapes (the template instantiations and tile shapes the benchmark configs run):
+    # config 3: multivariate K=3, M=4, R=64 -> z/chi/ssr_kernel<3,4>, statistics tiles MT=4 x 2 row blocks
+    "C3_MV_K3M4R64": ("mv", dict(seed=23, n=48, R=64, K=3, M=4)),
+    # config 4: covariate-adjusted (eta + xi), ragged grids, K=3 P=20 M=3 D=2, n_i in [150, 250] -> q = 36, 666 pairs
+    "C4_cov_ragged_K3P20M3D2": ("ragged", dict(seed=24, n=30, K=3, P=20, M=3, D=2, lo=150, hi=250)),
+    # config 5: high-dimensional functional, K=4, P=400 = 20 x 20 tensor-product cubic basis on a 32 x 32 grid, M=3
+    "C5_HD_K4P400M3": ("hd", dict(seed=25, n=8, K=4, M=3, side=32, p_side=20)),
+    # config 2 / the metric's shape: functional K=3 P=20 M=3 on a common 200-point grid
+    "C2_F_K3P20M3T200": ("common", dict(seed=22, n=64, T=200, K=3, P=20, M=3)),
 }
+# P = 400: the per-point P x P loops of the reference (and the oracle's pinv) take minutes, so the Gaussian
+# block draws of this case are pinned at beta = 1 only, and the live comparison with oracle/_ref is opt-in
+HEAVY_BLOCK_CASES = {"C5_HD_K4P400M3"}
+
+
+def block_betas(name):
+    return (1.0,) if name in HEAVY_BLOCK_CASES else (1.0, 0.6)
+
+
+BASELINE_CASES = ["C2_F_K3P20M3T200", "C3_MV_K3M4R64", "C4_cov_ragged_K3P20M3D2", "C5_HD_K4P400M3"]
 
 
 def build(name):
     kind, kw = CASES[name]
-    if kind == "common":
-        s = synth.functional_common(**kw)
+    if kind in ("common", "hd"):
+        s = synth.functional_common(**kw) if kind == "common" else synth.hd_common(**kw)
         n, T = s["n"], s["T"]
         off = np.arange(n + 1, dtype=np.int64) * T
         d = orc.Data(n=n, K=s["K"], P=s["P"], M=s["M"], y=s["y"].ravel(), B=np.tile(s["B"], (n, 1)), off=off, X=s["X"])

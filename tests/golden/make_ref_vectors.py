@@ -31,13 +31,15 @@ def main():
             out[key + "Z"] = ref.update_z(d, st, s["pi"], 1.3, cases.A_Z_PM, dr["gam"], dr["u"], beta, t)
             out[key + "chi"] = ref.update_chi(d, st, dr["eps"], beta, t)
             out[key + "sigma"] = ref.update_sigma(d, st, 1.0, 1.0, dr["gsig"], beta, t)
+            if beta not in cases.block_betas(name):
+                continue
             out[key + "nu"] = ref.update_nu(d, st, dr["tau"], Pm, dr["z_nu"], beta, t)
             out[key + "phi"] = ref.update_phi(d, st, dr["gamma"], dr["tilde_tau"], dr["z_phi"], beta, t)
             if d.D:
                 out[key + "eta"] = ref.update_eta(d, st, dr["tau_eta"], Pm, dr["z_eta"], beta, t)
                 out[key + "xi"] = ref.update_xi(d, st, dr["gamma_xi"], dr["tilde_tau_xi"], dr["z_xi"], beta, t)
         out[f"{name}|loglik"] = ref.loglik(d, st)
-        if not d.identity_basis and "P100" not in name:      # calcLikelihoodCPO over a short stored chain
+        if not d.identity_basis and "P100" not in name and name not in cases.HEAVY_BLOCK_CASES:      # calcLikelihoodCPO over a short stored chain
             out[f"{name}|cpo"] = ref.cpo(d, cases.stored_iterations(name, st))
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_updates.npz"), **out)
     print("wrote", len(out), "reference vectors")

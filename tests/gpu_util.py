@@ -9,7 +9,9 @@ from tests import cases
 def engine_for(name, device_basis=False, **kw):
     kind, _ = cases.CASES[name]
     s, d, st = cases.build(name)
-    if kind == "common":
+    if kind == "hd":      # BHDFMMM: the functional engine with the tensor-product basis (BFMMM.h:3069-3072)
+        eng = bf.Engine(model=FUNCTIONAL, n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], B=s["B"], T=s["T"], **kw)
+    elif kind == "common":
         if device_basis:
             eng = bf.Engine(model=FUNCTIONAL, n=s["n"], K=s["K"], P=s["P"], M=s["M"], y=s["y"], T=s["T"], t=s["t"],
                             degree=s["degree"], internal_knots=s["internal_knots"], boundary=s["boundary"], X=s["X"], **kw)

@@ -93,3 +93,28 @@ def multivariate(seed, n, R, K, M, D=0, sigma_sq=0.01):
     th = theta(par, Z, chi, X)
     y = np.asfortranarray(th + rng.normal(0, np.sqrt(sigma_sq), (n, R)))
     return dict(n=n, K=K, P=R, M=M, D=D, y=y, X=X, par=par, pi=pi, Z=Z, chi=chi)
+
+
+def tensor_design(t2, internal_per_dim, degree=3, boundary=(0.0, 1000.0)):
+    """Row-wise tensor product of two clamped B-spline bases (reference TensorBSpline, BSplines.h:18-62):
+    column index = i0 * P1 + i1 (dimension 0 slowest)."""
+    B0 = bspline_design(t2[:, 0], internal_per_dim[0], degree, boundary)
+    B1 = bspline_design(t2[:, 1], internal_per_dim[1], degree, boundary)
+    return (B0[:, :, None] * B1[:, None, :]).reshape(t2.shape[0], -1)
+
+
+def hd_common(seed, n, K, M, side=32, p_side=20, sigma_sq=0.01, degree=3):
+    """High-dimensional functional data (BHDFMMM, BASELINE config 5): a side x side grid on [0, 1000]^2 and
+    a p_side x p_side tensor-product cubic basis (P = p_side^2), shared by all functions."""
+    rng = np.random.default_rng(seed)
+    g = np.linspace(0.0, 1000.0, side)
+    t2 = np.stack(np.meshgrid(g, g, indexing="ij"), axis=-1).reshape(-1, 2)
+    ik = equispaced_internal(p_side, degree)
+    B = tensor_design(t2, (ik, ik), degree)
+    P, T = p_side * p_side, side * side
+    par = make_params(rng, K, P, M, 0, sigma_sq)
+    pi, Z, chi = make_state(rng, n, K, M)
+    th = theta(par, Z, chi)
+    y = th @ B.T + rng.normal(0, np.sqrt(sigma_sq), (n, T))
+    return dict(n=n, T=T, K=K, P=P, M=M, D=0, t=t2, internal_knots=ik, degree=degree, boundary=(0.0, 1000.0),
+                B=B, y=y, X=None, par=par, pi=pi, Z=Z, chi=chi, p_side=p_side, side=side)

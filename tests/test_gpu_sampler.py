@@ -120,6 +120,37 @@ def test_tempered_transition():
     smp.close(); eng.close()
 
 
+def test_tempered_rungs_use_the_tempered_sigma_shape_with_odd_grids():
+    """Inside a tempered transition every rung -- the beta = 1 rungs included -- draws sigma^2 with updateSigmaTempered's
+    shape a = sum_i beta n_i / 2 (real division, UpdateSigma.h:98-107; BFMMM.h:1556-1651), the plain sweep with
+    updateSigma's sum_i floor(n_i / 2) (UpdateSigma.h:49).  With an odd grid (T = 33) the two shapes differ by n / 2, i.e.
+    the sigma^2 draws of a flat ladder (beta = 1 everywhere) sit 16 / 16.5 = 3 % below those of plain sweeps at the same
+    SSR; a sigma^2 draw has a relative sd of 1 / sqrt(a) = 0.6 %, so the shift is unmistakable."""
+    s, eng, smp = _functional(seed=21, n=1500, T=33, K=2, P=7, M=2)
+    for _ in range(30):
+        smp.step(bf.SWEEP_FULL)
+    plain = []
+    for _ in range(12):
+        smp.step(bf.SWEEP_FULL)
+        plain.append(smp.get()["sigma_sq"])
+    N_t = 6
+    logA, ok = smp.tempered_transition(N_t, 1.0)
+    assert logA == 0.0 and ok
+    _, sig = smp.tt_trace(N_t)
+    ratio = np.mean(sig[1:]) / np.mean(plain)
+    assert 0.955 < ratio < 0.985, ratio
+    smp.close(); eng.close()
+
+
+def test_short_tape_fails_instead_of_returning_nan():
+    """An update that asks for more injected draws than the tape holds fails loudly (it used to return NaNs)."""
+    s, eng, smp = _functional(seed=22, n=64)
+    smp.tape(np.ones(3))
+    with pytest.raises(bf.EngineError):
+        smp.step(bf.SWEEP_FULL)
+    smp.close(); eng.close()
+
+
 def test_config1_sigma_matches_reference_stored_chain():
     """README example of the reference (Sim_data.RDS: n=40, T=100, K=2, P=7, M=3): the posterior of
     sigma^2 from our chain agrees with the reference's stored 150-draw chain

@@ -11,10 +11,10 @@ for spec in specs:
         if not os.path.exists(extra["BFMMM_LIB"]):
             print(spec, "missing"); continue
     env = dict(os.environ, **extra)
-    out = subprocess.run([sys.executable, "bench.py", "--steps", "60", "--warmup", "5", "--no-cpu-baseline"],
+    out = subprocess.run([sys.executable, "bench.py", "--steps", "60", "--warmup", "5", "--no-cpu-baseline", "--no-extras"],
                          capture_output=True, text=True, env=env, cwd=ROOT)
     line = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if not line:
-        print(spec, out.stderr[-400:]); continue
+        print(spec, out.stderr[-800:]); continue
     d = json.loads(line[-1])
-    print(f"{spec}: step {d['ms_per_step']*1e3:.0f}us e2e {d['e2e']['ms_per_step']*1e3:.0f}us", {k: round(v['ms']*1e3, 1) for k, v in d['roofline']['kernels'].items()})
+    print(f"{spec}: step {d['ms_per_step']*1e3:.0f}us e2e {d['e2e']['ms_per_step']*1e3:.0f}us", {k: round(v['ms']*1e3, 1) for k, v in d['roofline']['kernels'].items()}, flush=True)
