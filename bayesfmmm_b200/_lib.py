@@ -28,10 +28,10 @@ EXPORTS = [
     "bfmmm_update_z_async", "bfmmm_update_chi_async", "bfmmm_ssr_async", "bfmmm_suffstats_async",
     "bfmmm_read_stats", "bfmmm_clear_ssr_after", "bfmmm_sync", "bfmmm_stream", "bfmmm_engine_dims", "bfmmm_counts", "bfmmm_suffstats_ragged",
     # include/bfmmm_sampler.h
-    "bfmmm_hyper_defaults", "bfmmm_sampler_create", "bfmmm_sampler_create_detached", "bfmmm_sampler_destroy", "bfmmm_sampler_set_allreduce", "bfmmm_nccl_unique_id", "bfmmm_sampler_enable_nccl", "bfmmm_nccl_destroy", "bfmmm_p2p_create", "bfmmm_sampler_enable_p2p", "bfmmm_p2p_destroy", "bfmmm_sampler_set_hband", "bfmmm_sampler_set_counts",
+    "bfmmm_hyper_defaults", "bfmmm_sampler_create", "bfmmm_sampler_create_detached", "bfmmm_sampler_destroy", "bfmmm_sampler_device_resident", "bfmmm_sampler_set_allreduce", "bfmmm_nccl_unique_id", "bfmmm_sampler_enable_nccl", "bfmmm_nccl_destroy", "bfmmm_p2p_create", "bfmmm_sampler_enable_p2p", "bfmmm_p2p_destroy", "bfmmm_sampler_set_hband", "bfmmm_sampler_set_counts",
     "bfmmm_sampler_set", "bfmmm_sampler_get", "bfmmm_sampler_set_cov", "bfmmm_sampler_get_cov",
     "bfmmm_sampler_step", "bfmmm_sampler_run", "bfmmm_sampler_iteration", "bfmmm_sampler_last_accept",
-    "bfmmm_sampler_tape", "bfmmm_sampler_tape_left", "bfmmm_sampler_tempered_transition",
+    "bfmmm_sampler_tape", "bfmmm_sampler_tape_left", "bfmmm_sampler_set_tick", "bfmmm_sampler_tempered_transition",
     "bfmmm_sampler_run_mtt", "bfmmm_sampler_tt_trace", "bfmmm_sampler_record", "bfmmm_sampler_batches_written", "bfmmm_sampler_profile",
     # include/bfmmm_basis.h
     "bfmmm_bspline_basis", "bfmmm_tensor_bspline", "bfmmm_tensor_P", "bfmmm_get_P", "bfmmm_pmat_rw1",

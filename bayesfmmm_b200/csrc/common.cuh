@@ -26,6 +26,7 @@ struct PassArgs {
   int n, ld, P, D, QS;
   int P4;                           // P rounded up to 4: the cache and the globals carry zero rows P..P4-1 (common grid)
   int sm_count, max_blocks;         // launch geometry: persistent grid of at most max_blocks blocks
+  int grid_reserve;                 // blocks left out of the resident wave (a side-stream kernel occupies part of one SM)
   const double* __restrict__ Ct;    // common basis: whitened c~ ; ragged grids: least-squares c_i
   const double* __restrict__ Gl;    // ragged grids: lower band of G_i, row (j*P + p) = G_i[p-j][p]; else nullptr
   int bw;                           // ragged grids: band width (degree + 1)
@@ -41,6 +42,7 @@ struct PassArgs {
   double c_tot, trigam_a;           // 1 - log a + digamma(a) and trigamma(a) at a = a_Z_PM (host): lgamma(a sum_k z*_k) - lgamma(a sum_k z_k)
                                     // by its Taylor series around a, merged with the Stirling main terms (z_logratio_closed)
   double pi[8];
+  const double* __restrict__ zpar_dev;    // Z step: [pi (8) | alpha_3 | sigma^2] in device memory (device-resident sweep) or nullptr
   const double* __restrict__ gam;   // injected draws [K][ld] or nullptr (device RNG)
   const double* __restrict__ u;     // [ld] or nullptr
   const double* __restrict__ eps;   // chi: [M][ld] or nullptr

@@ -12,6 +12,7 @@
 
 #include "../../include/bfmmm.h"
 #include "common.cuh"
+#include "engine_internal.h"
 
 namespace bf { std::atomic<unsigned long long> g_launch_count{0}; }
 
@@ -600,14 +601,15 @@ static void polygamma01(double x, double& digam, double& trigam) {
 }
 
 static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta, bool injected,
-                    bool dump_draws) {
+                    bool dump_draws, const double* zpar_dev = nullptr) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
+  a.zpar_dev = zpar_dev;
   a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM); a.inv_a_Z_PM = 1.0 / a_Z_PM;
   double digam_a = 0;
   polygamma01(a_Z_PM, digam_a, a.trigam_a);
   a.c_tot = 1.0 - a.log_a_Z_PM + digam_a;
-  for (int k = 0; k < e->K; k++) a.pi[k] = pi[k];
+  for (int k = 0; k < e->K; k++) a.pi[k] = pi ? pi[k] : 0.0;
 #ifdef BF_TUNE_V
   static const bool force_inject = std::getenv("BFMMM_Z_INJECT") != nullptr;   // tuning: time the step without the RNG
   injected = injected || force_inject;
@@ -644,10 +646,16 @@ int bfmmm_update_z(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_
   return 0;
 }
 
-static int chi_launch(bfmmm_engine* e, double beta, bool injected) {
+static int chi_launch(bfmmm_engine* e, double beta, bool injected, const double* sigma_dev = nullptr) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
   if (e->sigma_armed) { a.sigma_dev = e->sigma_dev; e->sigma_armed = false; }
+  if (sigma_dev) {
+    a.sigma_dev = sigma_dev;
+    // device-resident sweep: the shrinkage-prior kernel of the side stream may still hold 4096 registers of one SM,
+    // and this kernel's blocks take all 65536: one block fewer keeps the whole grid resident from the start
+    a.grid_reserve = 1;
+  }
   if (injected) a.eps = e->draws;
   a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
   int rc = e->ragged ? bf::launch_chi_ragged(a, e->K, e->M, e->stream) : bf::launch_chi(a, e->K, e->M, e->stream);
@@ -945,6 +953,32 @@ int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
 }
 
 }  // extern "C"
+
+// ---- internal entry points of the device-resident sweep (engine_internal.h; not part of the C ABI)
+int bfmmm_engine_devinfo(bfmmm_engine* e, bf::EngineDevInfo* o) {
+  if (!e || !o) return fail("null argument");
+  o->stats = e->stats; o->glob = e->glob; o->Pc = e->Pc; o->P4 = (e->Pc + 3) & ~3; o->QS = e->QS; o->hbL = e->hbL;
+  o->L_host = e->L.data(); o->stream = e->stream; o->device = e->device; o->stats_len = e->stats_len;
+  return 0;
+}
+// Z step with pi, alpha_3 and sigma^2 read from device memory ([pi (8) | alpha_3 | sigma^2])
+int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const double* zpar_dev) {
+  if (!e || !zpar_dev) return fail("null argument");
+  CU(cudaSetDevice(e->device));
+  return z_launch(e, nullptr, 1.0, a_Z_PM, beta, false, false, zpar_dev);
+}
+// chi sweep with sigma^2 read from device memory
+int bfmmm_update_chi_async_p(bfmmm_engine* e, double beta, const double* sigma_dev) {
+  if (!e || !sigma_dev) return fail("null argument");
+  CU(cudaSetDevice(e->device));
+  return chi_launch(e, beta, false, sigma_dev);
+}
+// the value of sigma^2 the engine passes by value (marginal log-likelihood, Z step through the C ABI)
+int bfmmm_set_sigma(bfmmm_engine* e, double sigma_sq) {
+  if (!e || !(sigma_sq > 0)) return fail("bfmmm_set_sigma: bad argument");
+  e->sigma_sq = sigma_sq;
+  return 0;
+}
 
 namespace bf {
 int pass_grid(int ld, int v) { return (ld + PF_THREADS * v - 1) / (PF_THREADS * v); }

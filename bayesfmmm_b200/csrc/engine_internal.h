@@ -1,0 +1,23 @@
+// engine_internal.h -- entry points of engine.cu used by the sampler's device-resident sweep (host_sampler.cu).
+// C++ linkage, inside libbfmmm_b200.so only: not part of the C ABI of include/bfmmm.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bfmmm.h"
+
+namespace bf {
+struct EngineDevInfo {
+  double* stats;          // device statistics buffer [sum log Z (K) | accepts | ssr | ssr_after | W'W | C~'W ...]
+  int64_t stats_len;
+  double* glob;           // P4 x QS whitened global coefficients staged by the pass kernels
+  int Pc, P4, QS, hbL;    // rows of the projected cache (rank of the basis Gram), padded rows, feature stride, band of L
+  const double* L_host;   // P x Pc whitening factor (column-major, host)
+  cudaStream_t stream;
+  int device;
+};
+}  // namespace bf
+int bfmmm_engine_devinfo(bfmmm_engine* e, bf::EngineDevInfo* out);
+int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const double* zpar_dev);
+int bfmmm_update_chi_async_p(bfmmm_engine* e, double beta, const double* sigma_dev);
+int bfmmm_set_sigma(bfmmm_engine* e, double sigma_sq);

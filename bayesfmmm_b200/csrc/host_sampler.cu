@@ -18,15 +18,17 @@
 #include "../../include/bfmmm_io.h"
 #include "../../include/bfmmm_sampler.h"
 #include "common.cuh"
+#include "engine_internal.h"
+#include "globals_core.cuh"
+#include "globals_dev.h"
 
 namespace bf_host { bool chol_upper_rev(int n, const double* A, double* U, int hb); }
 
 namespace {
 
 // ------------------------------------------------------------------ host random numbers
-// purposes of the global Philox streams (one stream per purpose and iteration)
-enum { HP_PI = 101, HP_ALPHA3, HP_PHI, HP_DELTA, HP_A, HP_GAMMA, HP_NU, HP_TAU, HP_SIGMA, HP_ETA, HP_XI,
-       HP_TAU_ETA, HP_DELTA_XI, HP_A_XI, HP_GAMMA_XI, HP_TT };
+// (the purposes of the global Philox streams, HP_*, live in globals_core.cuh)
+using namespace bf;   // HP_*, GlobalsView, core_update_*
 
 struct HostRng {
   uint64_t key = 0, iteration = 0;
@@ -39,9 +41,29 @@ struct HostRng {
     if (tape.empty()) { tape_underrun = true; return std::numeric_limits<double>::quiet_NaN(); }
     double v = tape.front(); tape.pop_front(); return v;
   }
-  double normal() { return use_tape ? pop() : stream.normal(); }
   double uniform() { return use_tape ? pop() : stream.uniform(); }
   double gamma(double shape) { return use_tape ? pop() : stream.gamma(shape); }   // Gamma(shape, 1)
+};
+// the interface globals_core.cuh's templates draw through: a stream per (purpose, element), or the tape of injected
+// draws (consumed in call order, the element is ignored)
+struct HostStreamRef {
+  HostRng* r;
+  bf::RngStream st;
+#ifdef __CUDA_ARCH__
+  __host__ __device__ double normal() { return 0; }
+  __host__ __device__ double uniform() { return 0; }
+  __host__ __device__ double gamma(double) { return 0; }
+#else
+  __host__ __device__ double normal() { return r->use_tape ? r->pop() : st.normal(); }
+  __host__ __device__ double uniform() { return r->use_tape ? r->pop() : st.uniform(); }
+  __host__ __device__ double gamma(double shape) { return r->use_tape ? r->pop() : st.gamma(shape); }
+#endif
+};
+struct HostRngAdapter {
+  HostRng* r;
+  __host__ __device__ HostStreamRef open(uint32_t purpose, uint64_t element) const {
+    return HostStreamRef{r, bf::RngStream(r->key, 0xB200ull + (element << 16), r->iteration, purpose)};
+  }
 };
 
 // ------------------------------------------------------------------ small dense linear algebra (column-major)
@@ -141,46 +163,7 @@ int half_bandwidth(int n, const double* A) {
   return hb;
 }
 
-double lgamma_d(double x) { return std::lgamma(x); }
-double pnorm_std(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
-double qnorm_std(double p) {          // Acklam's rational approximation + Halley refinement
-  if (p <= 0) return -std::numeric_limits<double>::infinity();
-  if (p >= 1) return std::numeric_limits<double>::infinity();
-  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
-                             1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
-  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
-                             6.680131188771972e+01, -1.328068155288572e+01};
-  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
-                             -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
-  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
-                             3.754408661907416e+00};
-  double q, r, x;
-  if (p < 0.02425) { q = std::sqrt(-2 * std::log(p));
-    x = (((((c[0]*q+c[1])*q+c[2])*q+c[3])*q+c[4])*q+c[5]) / ((((d[0]*q+d[1])*q+d[2])*q+d[3])*q+1);
-  } else if (p <= 1 - 0.02425) { q = p - 0.5; r = q * q;
-    x = (((((a[0]*r+a[1])*r+a[2])*r+a[3])*r+a[4])*r+a[5])*q / (((((b[0]*r+b[1])*r+b[2])*r+b[3])*r+b[4])*r+1);
-  } else { q = std::sqrt(-2 * std::log(1 - p));
-    x = -(((((c[0]*q+c[1])*q+c[2])*q+c[3])*q+c[4])*q+c[5]) / ((((d[0]*q+d[1])*q+d[2])*q+d[3])*q+1);
-  }
-  for (int it = 0; it < 2; it++) {
-    double e = pnorm_std(x) - p;
-    double u = e * std::sqrt(2 * 3.14159265358979323846) * std::exp(x * x / 2);
-    x = x - u / (1 + x * u / 2);
-  }
-  return x;
-}
-// truncated normal on [lo, inf): inverse-CDF draw from one uniform; log density
-double rtruncnorm_lo(double mean, double sd, double lo, double u) {
-  double pa = pnorm_std((lo - mean) / sd);
-  return mean + sd * qnorm_std(pa + u * (1.0 - pa));
-}
-double dtruncnorm_lo_log(double x, double mean, double sd, double lo) {
-  if (x < lo) return -std::numeric_limits<double>::infinity();
-  const double LN_SQRT_2PI = 0.918938533204672741780329736406;
-  double z = (x - mean) / sd;
-  double scale = 1.0 - pnorm_std((lo - mean) / sd);
-  return -(LN_SQRT_2PI + 0.5 * z * z + std::log(sd)) - std::log(scale);
-}
+// (normal / truncated-normal helpers: g_pnorm, g_qnorm, g_rtruncnorm_lo, g_dtruncnorm_lo_log in globals_core.cuh)
 
 int sfail(const std::string& m) { return bf::set_error(m.c_str()); }
 
@@ -201,6 +184,8 @@ struct bfmmm_sampler {
   std::vector<std::vector<double>> pre_prior; // scaled penalty matrices of the nu / eta blocks (kept: 1.3 MB each at P = 400)
   std::vector<double> prior_buf;
   int pre_next = -1;                        // next prefactored block (-1: none)
+  uint32_t blk_purpose = 0;                 // stream (purpose, block index) of the next block draw's normals
+  uint64_t blk_index = 0;
   int hbG = 0, hbP = 0;     // half bandwidths of the basis Gram and of the penalty matrix (block draws)
   const double* Hb = nullptr;   // ragged grids: pair cross-Gram band (set before the block draws)
   vecd Hb_own;
@@ -233,7 +218,27 @@ struct bfmmm_sampler {
     std::vector<vecd> nu, Phi, pi, delta, gamma, A, tau, Z, chi, eta, xi, tau_eta, delta_xi, gamma_xi, A_xi;
     vecd sigma, alpha3;
   } rec;
-  vecd work, Prec, C, Lc, rhs, v1, v2;
+  vecd work, Prec, C, Lc, rhs, v1, v2, zdraw;
+  // ---- device-resident sweep (globals_kernels.cu): the chain's globals live in device memory, the sweep is a queue
+  // of kernels, the host vectors above are a mirror refreshed on demand (dev_pull)
+  struct Dev {
+    bool on = false;          // the sampler runs its sweeps on the device
+    bool host_stale = false;  // the device holds newer values than the host vectors
+    bool dev_stale = true;    // the host vectors hold newer values than the device (set / host updates / restore)
+    double* par = nullptr;    // [nu | Phi | pi (8) | alpha3 | sigma_sq | delta | gamma | A | tau] (device)
+    double* cst = nullptr;    // [G | Pmat | L] (device)
+    int* err = nullptr;       // device flag: a block precision was not positive definite
+    long long* clk = nullptr; // BFMMM_DRAW_CLK=1: phase time stamps of the block-draw kernel (tuning)
+    vecd h_par;               // host staging of `par`
+    size_t o_nu = 0, o_Phi = 0, o_pi = 0, o_alpha3 = 0, o_sigma = 0, o_delta = 0, o_gamma = 0, o_A = 0, o_tau = 0, len = 0;
+    size_t c_G = 0, c_P = 0, c_L = 0;
+    int hbmax = 0;
+    bf::EngineDevInfo info{};
+    cudaStream_t side = nullptr;          // stream of the priors kernel
+    cudaEvent_t ev_drawn = nullptr, ev_priors = nullptr, ev_stats = nullptr, ev_pi = nullptr;
+    bool priors_pending = false, pi_pending = false;
+    bool ll_from_ssr = false;             // the last sweep had no chi step: its log-likelihood comes from the SSR slot
+  } dev;
 
   double& nu_(int k, int p) { return nu[(size_t)p * K + k]; }
   double& Phi_(int k, int p, int m) { return Phi[((size_t)m * P + p) * K + k]; }
@@ -256,6 +261,25 @@ int tape_check(bfmmm_sampler* s) {
   if (!s->rng.tape_underrun) return 0;
   s->rng.tape_underrun = false;
   return sfail("the tape of injected draws ran out (bfmmm_sampler_tape holds fewer values than the update consumes)");
+}
+
+GlobalsView host_view(bfmmm_sampler* s) {
+  GlobalsView g;
+  g.K = s->K; g.P = s->P; g.M = s->M; g.identity = s->identity ? 1 : 0; g.hbP = s->hbP;
+  g.nu = s->nu.data(); g.Phi = s->Phi.data(); g.pi = s->pi.data(); g.delta = s->delta.data(); g.gamma = s->gamma.data();
+  g.A = s->A.data(); g.tau = s->tau.data(); g.alpha3 = &s->alpha3;
+  g.Pmat = s->Pmat.empty() ? nullptr : s->Pmat.data();
+  g.h = s->h; g.n_total = (double)s->n_total;
+  return g;
+}
+int dev_pull(bfmmm_sampler* s);
+// a host-side update on a sampler whose chain lives on the device: fetch the current values first, and remember
+// that the device copy is out of date afterwards
+int dev_begin_host_update(bfmmm_sampler* s) {
+  if (!s->dev.on) return 0;
+  if (dev_pull(s)) return 1;
+  s->dev.dev_stale = true;
+  return 0;
 }
 
 // the chain's global parameters: what a rejected tempered transition restores (BFMMM.h:1631-1651)
@@ -340,10 +364,72 @@ void prefactor_blocks(bfmmm_sampler* s, const std::vector<PreBlock>& blocks, con
   for (auto& x : th) x.join();
 }
 
+// the P standard normals of the next block draw: element (block index, coefficient) of the update's stream -- or the
+// values generated ahead while the device was busy (zpre), or the tape of injected draws
+void block_normals(bfmmm_sampler* s, double* z) {
+  const int P = s->P;
+  if (s->zpre_on) { for (int p = 0; p < P; p++) z[p] = s->zpre[s->zpre_pos++]; }
+  else {
+    HostRngAdapter r{&s->rng};
+    for (int p = 0; p < P; p++) { auto st = r.open(s->blk_purpose, (s->blk_index << 12) + (uint64_t)p); z[p] = st.normal(); }
+  }
+  s->blk_index++;
+}
+// Small P on a common basis: the band-storage factorisation and solves of globals_core.cuh, i.e. the statements the
+// device-resident sweep runs (draw_blocks_kernel).  Returns -1 when the precision is not positive definite (the
+// caller then takes the pseudo-inverse route of the reference).
+int block_draw_band(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const double* BtYW, double beta,
+                    const double* prior_full, const double* prior_diag, const double* z) {
+  const int P = s->P, q = s->q, a = s->feat(k, mm, dd);
+  const double sc = beta / s->sigma_sq;
+  const int hg = s->identity ? 0 : s->hbG, hb = std::max(hg, prior_full ? s->hbP : 0), ldb = hb + 1;
+  s->v1.assign(P, 0.0); s->v2.resize(P); s->rhs.resize(P);
+  for (int kk = 0; kk < s->K; kk++)
+    for (int m2 = 0; m2 <= s->M; m2++)
+      for (int d2 = 0; d2 <= s->D; d2++) {
+        const int b = s->feat(kk, m2, d2);
+        if (b == a) continue;
+        const double sab = WtW[(size_t)b * q + a];
+        get_coef(s, kk, m2, d2, s->v2.data());
+        for (int p = 0; p < P; p++) s->v1[p] += sab * s->v2[p];
+      }
+  for (int r = 0; r < P; r++) {
+    double gv = 0;
+    if (s->identity) gv = s->v1[r];
+    else for (int c = std::max(0, r - hg); c <= std::min(P - 1, r + hg); c++) gv += s->G[(size_t)r * P + c] * s->v1[c];
+    s->rhs[r] = sc * (BtYW[(size_t)a * P + r] - gv);
+  }
+  const double saa = WtW[(size_t)a * q + a];
+  s->work.resize((size_t)P * ldb + 3 * (size_t)P);
+  double* A = s->work.data();
+  double *rd = A + (size_t)P * ldb, *w = rd + P, *x = w + P;
+  for (int i = 0; i < P; i++)
+    for (int d = 0; d <= hb; d++) {
+      const int c = i + d;
+      double v = 0;
+      if (c < P) {
+        const double g = s->identity ? (d == 0 ? 1.0 : 0.0) : s->G[(size_t)c * P + i];
+        const double pr = prior_full ? prior_full[(size_t)c * P + i] : (d == 0 ? prior_diag[i] : 0.0);
+        v = sc * saa * g + pr;
+      }
+      A[(size_t)i * ldb + d] = v;
+    }
+  if (!band_chol_upper_rev_rd(P, hb, ldb, A, A, rd)) return -1;
+  band_draw_rd(P, hb, ldb, A, rd, s->rhs.data(), z, x, w);
+  set_coef(s, k, mm, dd, x);
+  return 0;
+}
+
 int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const double* BtYW, double beta,
                const double* prior_full, const double* prior_diag) {
   const int P = s->P, q = s->q;
   const int a = s->feat(k, mm, dd);
+  s->zdraw.resize(P);
+  block_normals(s, s->zdraw.data());
+  if (!s->ragged && P < PREFACTOR_MIN_P) {
+    const int rc = block_draw_band(s, k, mm, dd, WtW, BtYW, beta, prior_full, prior_diag, s->zdraw.data());
+    if (rc >= 0) return rc;
+  }
   s->Prec.resize((size_t)P * P); s->C.resize((size_t)P * P); s->Lc.resize((size_t)P * P);
   s->rhs.resize(P); s->v1.resize(P); s->v2.resize(P);
   const double sc = beta / s->sigma_sq;
@@ -410,8 +496,7 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
   }
   const int hb = s->ragged ? std::max(s->bw - 1, prior_full ? s->hbP : 0) : std::max(s->identity ? 0 : s->hbG, prior_full ? s->hbP : 0);
   s->work.resize((size_t)2 * P * P);
-  if (s->zpre_on) { for (int p = 0; p < P; p++) s->v2[p] = s->zpre[s->zpre_pos++]; }
-  else for (int p = 0; p < P; p++) s->v2[p] = s->rng.normal();
+  for (int p = 0; p < P; p++) s->v2[p] = s->zdraw[p];
   double* U = s->work.data();
   const bool pre = !s->ragged && s->pre_next >= 0 && s->pre_next < (int)s->pre_U.size();
   const bool pre_good = pre && s->pre_ok[s->pre_next];
@@ -445,12 +530,6 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
   }
   set_coef(s, k, mm, dd, s->v1.data());
   return 0;
-}
-
-double calc_lB(const double* al, int K) {
-  double lB = 0, tot = 0;
-  for (int k = 0; k < K; k++) { lB += lgamma_d(al[k]); tot += al[k]; }
-  return lB - lgamma_d(tot);
 }
 
 inline double now_s() {
@@ -490,6 +569,10 @@ void set_loglik(bfmmm_sampler* s, double ssr_ll, double sigma_sq) {
 // completes a deferred log-likelihood outside a sweep (bfmmm_sampler_get, tempered transitions)
 int flush_loglik(bfmmm_sampler* s) {
   if (!s->ll_pending || !s->e) return 0;
+  if (s->dev.on) {                        // sigma^2 of the sweep is on the device
+    if (dev_pull(s)) return 1;
+    s->ll_sigma = s->sigma_sq;
+  }
   struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
   double* dev = nullptr; int64_t len = 0;
   if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
@@ -502,6 +585,7 @@ int flush_loglik(bfmmm_sampler* s) {
   // the slot now holds the global sum on every rank: zero it so the next full exchange does not add it again
   return bfmmm_clear_ssr_after(s->e);
 }
+int record_iteration_fwd(bfmmm_sampler* s);
 const double* st_slz(bfmmm_sampler* s) { return s->stats.data(); }
 double st_acc(bfmmm_sampler* s) { return s->stats[s->K]; }
 double st_ssr(bfmmm_sampler* s) { return s->stats[s->K + 1]; }
@@ -509,6 +593,227 @@ double st_ssr_after(bfmmm_sampler* s) { return s->stats[s->K + 2]; }
 const double* st_wtw(bfmmm_sampler* s) { return s->stats.data() + s->K + 3; }
 const double* st_btyw(bfmmm_sampler* s) { return s->stats.data() + s->K + 3 + (size_t)s->q * s->q; }
 const double* st_hb(bfmmm_sampler* s) { return s->stats.data() + s->K + 3 + (size_t)s->q * s->q + (size_t)s->P * s->q; }
+
+
+// ================================================================= device-resident sweep
+// The chain's globals live in device memory (s->dev.par); a sweep is a queue of kernels on the engine's stream -- the
+// pass kernels, the Gaussian block draws, the sigma^2 / pi / alpha_3 draws -- plus the shrinkage priors on a side
+// stream (they feed the next sweep's block draws and overlap this sweep's SSR and chi passes).  Nothing is read back
+// unless the caller asks (bfmmm_sampler_get, the recorder, a tempered transition).
+#define CUS(x)                                                                          \
+  do {                                                                                  \
+    cudaError_t _e = (x);                                                               \
+    if (_e != cudaSuccess) return sfail(std::string(#x) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr size_t DEV_MAX_BAND_DOUBLES = 16384;      // nb * P * (hb + 2) doubles of factors the draw kernel keeps in shared memory
+
+bool dev_eligible(const bfmmm_sampler* s) {
+  if (!s->e || s->D > 0 || s->ragged || s->K > 8) return false;
+  // Opt-in (BFMMM_DEVICE_GLOBALS=1): measured on B200 the single-block draw kernel is latency bound (52 us against the
+  // 31 us the host spends on the same draws), so the host-drawn globals stay the default.
+  if (!std::getenv("BFMMM_DEVICE_GLOBALS") || std::getenv("BFMMM_HOST_GLOBALS")) return false;
+  const int hb = std::max(s->identity ? 0 : s->hbG, s->identity ? 0 : s->hbP);
+  const size_t nb = (size_t)s->K * (s->M + 1);
+  if (hb > 0 && s->P > 30) return false;      // banded precisions: one warp per block, a row of T_a in a lane's registers
+  return nb * s->P * (hb + 5) <= DEV_MAX_BAND_DOUBLES;
+}
+int dev_init(bfmmm_sampler* s) {
+  auto& d = s->dev;
+  if (bfmmm_engine_devinfo(s->e, &d.info)) return 1;
+  CUS(cudaSetDevice(d.info.device));
+  const size_t K = s->K, P = s->P, M = s->M;
+  size_t o = 0;
+  d.o_nu = o; o += K * P;
+  d.o_Phi = o; o += K * P * M;
+  d.o_pi = o; o += 8;                 // [pi (8) | alpha3 | sigma_sq] is what the Z kernel reads
+  d.o_alpha3 = o; o += 1;
+  d.o_sigma = o; o += 1;
+  d.o_delta = o; o += K * M;
+  d.o_gamma = o; o += K * P * M;
+  d.o_A = o; o += 2 * K;
+  d.o_tau = o; o += K;
+  d.len = o;
+  d.h_par.assign(d.len, 0.0);
+  CUS(cudaMalloc(&d.par, d.len * 8));
+  CUS(cudaMalloc(&d.err, 4));
+  CUS(cudaMemset(d.err, 0, 4));
+  if (std::getenv("BFMMM_DRAW_CLK")) { CUS(cudaMalloc(&d.clk, 16 * 8)); CUS(cudaMemset(d.clk, 0, 16 * 8)); }
+  const size_t Pc = d.info.Pc;
+  d.c_G = 0; d.c_P = P * P; d.c_L = 2 * P * P;
+  vecd cst(2 * P * P + P * Pc, 0.0);
+  std::copy(s->G.begin(), s->G.end(), cst.begin() + d.c_G);
+  if (!s->Pmat.empty()) std::copy(s->Pmat.begin(), s->Pmat.end(), cst.begin() + d.c_P);
+  if (!s->identity) std::copy(d.info.L_host, d.info.L_host + P * Pc, cst.begin() + d.c_L);
+  CUS(cudaMalloc(&d.cst, cst.size() * 8));
+  CUS(cudaMemcpy(d.cst, cst.data(), cst.size() * 8, cudaMemcpyHostToDevice));
+  d.hbmax = std::max(s->identity ? 0 : s->hbG, s->identity ? 0 : s->hbP);
+  CUS(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
+  CUS(cudaEventCreateWithFlags(&d.ev_drawn, cudaEventDisableTiming));
+  CUS(cudaEventCreateWithFlags(&d.ev_priors, cudaEventDisableTiming));
+  CUS(cudaEventCreateWithFlags(&d.ev_stats, cudaEventDisableTiming));
+  CUS(cudaEventCreateWithFlags(&d.ev_pi, cudaEventDisableTiming));
+  d.on = true; d.dev_stale = true; d.host_stale = false;
+  return 0;
+}
+void dev_free(bfmmm_sampler* s) {
+  auto& d = s->dev;
+  if (!d.par && !d.cst) return;
+  cudaSetDevice(d.info.device);
+  if (d.side) { cudaStreamSynchronize(d.side); cudaStreamDestroy(d.side); }
+  if (d.clk) {
+    long long c[16];
+    if (cudaMemcpy(c, d.clk, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      std::fprintf(stderr, "draw_blocks_kernel phases (cycles):");
+      for (int i = 1; i < 8; i++) std::fprintf(stderr, " %lld", c[i] - c[i - 1]);
+      std::fprintf(stderr, "\n");
+    }
+    cudaFree(d.clk);
+  }
+  if (d.ev_drawn) cudaEventDestroy(d.ev_drawn);
+  if (d.ev_priors) cudaEventDestroy(d.ev_priors);
+  if (d.ev_stats) cudaEventDestroy(d.ev_stats);
+  if (d.ev_pi) cudaEventDestroy(d.ev_pi);
+  cudaFree(d.par); cudaFree(d.cst); cudaFree(d.err);
+  d = bfmmm_sampler::Dev();
+}
+GlobalsView dev_view(bfmmm_sampler* s) {
+  auto& d = s->dev;
+  GlobalsView g = host_view(s);
+  g.nu = d.par + d.o_nu; g.Phi = d.par + d.o_Phi; g.pi = d.par + d.o_pi; g.delta = d.par + d.o_delta;
+  g.gamma = d.par + d.o_gamma; g.A = d.par + d.o_A; g.tau = d.par + d.o_tau; g.alpha3 = d.par + d.o_alpha3;
+  g.Pmat = s->identity ? nullptr : d.cst + d.c_P;
+  return g;
+}
+// host vectors -> device (after bfmmm_sampler_set, a host-side update or a restored tempered transition)
+int dev_push(bfmmm_sampler* s) {
+  auto& d = s->dev;
+  if (!d.on || !d.dev_stale) return 0;
+  CUS(cudaSetDevice(d.info.device));
+  // the staging buffer may still be travelling from an earlier push
+  CUS(cudaStreamSynchronize(d.info.stream));
+  double* h = d.h_par.data();
+  std::copy(s->nu.begin(), s->nu.end(), h + d.o_nu);
+  std::copy(s->Phi.begin(), s->Phi.end(), h + d.o_Phi);
+  std::fill(h + d.o_pi, h + d.o_pi + 8, 0.0);
+  std::copy(s->pi.begin(), s->pi.end(), h + d.o_pi);
+  h[d.o_alpha3] = s->alpha3; h[d.o_sigma] = s->sigma_sq;
+  std::copy(s->delta.begin(), s->delta.end(), h + d.o_delta);
+  std::copy(s->gamma.begin(), s->gamma.end(), h + d.o_gamma);
+  std::copy(s->A.begin(), s->A.end(), h + d.o_A);
+  std::copy(s->tau.begin(), s->tau.end(), h + d.o_tau);
+  if (d.priors_pending) { CUS(cudaStreamWaitEvent(d.info.stream, d.ev_priors, 0)); d.priors_pending = false; }
+  if (d.pi_pending) { CUS(cudaStreamWaitEvent(d.info.stream, d.ev_pi, 0)); d.pi_pending = false; }
+  CUS(cudaMemcpyAsync(d.par, h, d.len * 8, cudaMemcpyHostToDevice, d.info.stream));
+  if (push_globals(s)) return 1;             // the whitened coefficients of the pass kernels
+  d.dev_stale = false;
+  return 0;
+}
+// device -> host vectors (get, recorder, tempered transitions, host-side updates)
+int dev_pull(bfmmm_sampler* s) {
+  auto& d = s->dev;
+  if (!d.on || !d.host_stale) return 0;
+  CUS(cudaSetDevice(d.info.device));
+  CUS(cudaStreamSynchronize(d.side));
+  CUS(cudaStreamSynchronize(d.info.stream));
+  int err = 0;
+  CUS(cudaMemcpy(&err, d.err, 4, cudaMemcpyDeviceToHost));
+  if (err) return sfail("device block draw: a precision matrix is not positive definite (BFMMM_HOST_GLOBALS=1 selects the host draws with the reference's pseudo-inverse route)");
+  CUS(cudaMemcpy(d.h_par.data(), d.par, d.len * 8, cudaMemcpyDeviceToHost));
+  const double* h = d.h_par.data();
+  std::copy(h + d.o_nu, h + d.o_nu + s->nu.size(), s->nu.begin());
+  std::copy(h + d.o_Phi, h + d.o_Phi + s->Phi.size(), s->Phi.begin());
+  std::copy(h + d.o_pi, h + d.o_pi + s->pi.size(), s->pi.begin());
+  s->alpha3 = h[d.o_alpha3]; s->sigma_sq = h[d.o_sigma];
+  std::copy(h + d.o_delta, h + d.o_delta + s->delta.size(), s->delta.begin());
+  std::copy(h + d.o_gamma, h + d.o_gamma + s->gamma.size(), s->gamma.begin());
+  std::copy(h + d.o_A, h + d.o_A + s->A.size(), s->A.begin());
+  std::copy(h + d.o_tau, h + d.o_tau + s->tau.size(), s->tau.begin());
+  if (bfmmm_set_sigma(s->e, s->sigma_sq)) return 1;
+  // acceptance count and SSR of the last sweep (local shard unless the exchange already summed them)
+  vecd st(s->K + 3);
+  if (bfmmm_read_stats(s->e, st.data(), s->K + 3)) return 1;
+  s->last_accept = (int64_t)std::llround(st[s->K]);
+  if ((int64_t)s->stats.size() < s->K + 3) s->stats.resize(s->K + 3);
+  std::copy(st.begin(), st.end(), s->stats.begin());
+  d.host_stale = false;
+  if (d.ll_from_ssr) {                 // Nu_Z sweeps: calcLikelihood on the SSR of the sigma^2 step (already summed over shards)
+    s->last_ssr = st[s->K + 1];
+    set_loglik(s, s->last_ssr, s->sigma_sq);
+  }
+  return 0;
+}
+
+int sampler_step_device(bfmmm_sampler* s, int sweep, double beta) {
+  auto& d = s->dev;
+  bfmmm_engine* e = s->e;
+  const bool do_z = (sweep == BFMMM_SWEEP_NU_Z || sweep == BFMMM_SWEEP_FULL);
+  const bool do_phi = (sweep == BFMMM_SWEEP_THETA || sweep == BFMMM_SWEEP_FULL);
+  const bool do_nu = do_z, do_chi = do_phi;
+  const bool tempered = s->in_tt || beta != 1.0;
+  s->rng.iteration = (uint64_t)s->tick;
+  CUS(cudaSetDevice(d.info.device));
+  if (dev_push(s)) return 1;
+  if (bfmmm_seed(e, s->rng.key, (uint64_t)s->tick)) return 1;
+  cudaStream_t st = d.info.stream;
+  const double* zpar = d.par + d.o_pi;
+  double* sigma_dev = d.par + d.o_sigma;
+  const StreamRng rng{s->rng.key, (uint64_t)s->tick};
+  if (d.pi_pending) { CUS(cudaStreamWaitEvent(st, d.ev_pi, 0)); d.pi_pending = false; }     // last sweep's pi, alpha_3
+  if (do_z && bfmmm_update_z_async_p(e, s->h.a_Z_PM, beta, zpar)) return 1;          // updateZ_PM
+  if (bfmmm_suffstats_async(e)) return 1;
+  if (s->allreduce && s->allreduce(s->allreduce_ctx, d.info.stats, d.info.stats_len, st)) return sfail("all-reduce hook failed");
+  CUS(cudaEventRecord(d.ev_stats, st));
+  // updatePhi, updateNu: the blocks need last sweep's delta, gamma, tau (side stream)
+  if (d.priors_pending) { CUS(cudaStreamWaitEvent(st, d.ev_priors, 0)); d.priors_pending = false; }
+  DrawArgs da;
+  da.g = dev_view(s);
+  da.Pc = d.info.Pc; da.P4 = d.info.P4; da.QS = d.info.QS; da.q = s->q;
+  da.hbG = s->identity ? 0 : s->hbG; da.hbL = d.info.hbL; da.hbmax = d.hbmax;
+  da.G = s->identity ? nullptr : d.cst + d.c_G; da.L = s->identity ? nullptr : d.cst + d.c_L;
+  da.stats = d.info.stats; da.glob = d.info.glob; da.sigma_dev = sigma_dev; da.beta = beta;
+  da.do_phi = do_phi ? 1 : 0; da.do_nu = do_nu ? 1 : 0; da.rng = rng; da.err = d.err;
+  da.clk = d.clk;
+  if (launch_draw_blocks(da, st)) return sfail("draw_blocks kernel launch failed");
+  CUS(cudaEventRecord(d.ev_drawn, st));
+  if (bfmmm_ssr_async(e)) return 1;                                                 // updateSigma's data pass, new globals
+  if (s->allreduce && s->allreduce(s->allreduce_ctx, d.info.stats + s->K + 1, 1, st)) return sfail("all-reduce hook failed");
+  SigmaPiArgs sa;
+  sa.g = da.g; sa.stats = d.info.stats; sa.sigma_dev = sigma_dev;
+  sa.shape = tempered ? (beta * s->n_points_total) / 2 + s->h.alpha_0 : s->sum_half_total + s->h.alpha_0;
+  sa.scale_ssr = tempered ? beta / 2 : 0.5;
+  sa.do_pi = do_z ? 1 : 0; sa.rng = rng;
+  if (launch_sigma(sa, st)) return sfail("sigma kernel launch failed");              // updateSigma
+  if (do_chi && bfmmm_update_chi_async_p(e, beta, sigma_dev)) return 1;             // updateChi (+ the SSR calcLikelihood needs)
+  // side stream: updatePi_PM, updateAlpha3 (they only need the reduced sum_i log Z_ik), then, behind the block draws,
+  // updateDelta, updateA, updateGamma, updateTau
+  if (do_z) {
+    CUS(cudaStreamWaitEvent(d.side, d.ev_stats, 0));
+    if (launch_pi_alpha(sa, d.side)) return sfail("pi / alpha_3 kernel launch failed");
+    CUS(cudaEventRecord(d.ev_pi, d.side));
+    d.pi_pending = true;
+  }
+  CUS(cudaStreamWaitEvent(d.side, d.ev_drawn, 0));
+  PriorsArgs pa;
+  pa.g = da.g; pa.do_phi = do_phi ? 1 : 0; pa.rng = rng;
+  if (launch_priors(pa, d.side)) return sfail("priors kernel launch failed");
+  CUS(cudaEventRecord(d.ev_priors, d.side));
+  d.priors_pending = true;
+  d.host_stale = true;
+  s->ll_pending = do_chi; s->ll_sigma = 0.0;                 // sigma^2 is on the device: flush_loglik pulls it
+  d.ll_from_ssr = !do_chi;
+  s->tick++;
+  if (s->in_tt || s->rec.on) {
+    if (dev_pull(s)) return 1;
+    if (do_chi && flush_loglik(s)) return 1;
+
+  }
+  if (!s->in_tt) {
+    if (s->rec.on && record_iteration_fwd(s)) return 1;
+    s->iteration++;
+  }
+  return 0;
+}
 
 }  // namespace
 
@@ -564,6 +869,7 @@ int bfmmm_sampler_create(bfmmm_engine* e, const bfmmm_hyper* h, int64_t n_total,
                                                        // set the totals with bfmmm_sampler_set_counts
   s->n_points_total = npts * ratio;
   s->sum_half_total = s->identity ? (double)(((int64_t)s->n_total * s->P) / 2) : sum_half * ratio;
+  if (dev_eligible(s) && dev_init(s)) { delete s; return 1; }
   *out = s;
   return 0;
 }
@@ -582,7 +888,12 @@ int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int
   *out = s;
   return 0;
 }
-void bfmmm_sampler_destroy(bfmmm_sampler* s) { delete s; }
+void bfmmm_sampler_destroy(bfmmm_sampler* s) {
+  if (s) dev_free(s);
+  delete s;
+}
+// 1 when the sampler's sweeps run device-resident (globals_kernels.cu), 0 when the host draws the globals
+int bfmmm_sampler_device_resident(bfmmm_sampler* s) { return s && s->dev.on ? 1 : 0; }
 // ragged grids: pair cross-Gram band for the bfmmm_host_update_{phi,nu,eta,xi} calls that follow
 // (copied); bfmmm_sampler_step sets it from the device statistics itself
 int bfmmm_sampler_set_hband(bfmmm_sampler* s, const double* Hband) {
@@ -611,6 +922,7 @@ int bfmmm_sampler_set(bfmmm_sampler* s, const double* nu, const double* Phi, con
                       const double* pi, const double* alpha3, const double* delta, const double* gamma,
                       const double* A, const double* tau) {
   if (!s) return sfail("null sampler");
+  if (dev_begin_host_update(s)) return 1;
   CP_IN(s->nu, nu); CP_IN(s->Phi, Phi); CP_IN(s->pi, pi); CP_IN(s->delta, delta); CP_IN(s->gamma, gamma);
   CP_IN(s->A, A); CP_IN(s->tau, tau);
   if (sigma_sq) s->sigma_sq = *sigma_sq;
@@ -620,6 +932,7 @@ int bfmmm_sampler_set(bfmmm_sampler* s, const double* nu, const double* Phi, con
 int bfmmm_sampler_get(bfmmm_sampler* s, double* nu, double* Phi, double* sigma_sq, double* pi,
                       double* alpha3, double* delta, double* gamma, double* A, double* tau, double* loglik) {
   if (!s) return sfail("null sampler");
+  if (dev_pull(s)) return 1;
   if (loglik && flush_loglik(s)) return 1;
   CP_OUT(nu, s->nu); CP_OUT(Phi, s->Phi); CP_OUT(pi, s->pi); CP_OUT(delta, s->delta); CP_OUT(gamma, s->gamma);
   CP_OUT(A, s->A); CP_OUT(tau, s->tau);
@@ -644,89 +957,54 @@ int bfmmm_sampler_get_cov(bfmmm_sampler* s, double* eta, double* xi, double* tau
 }
 int bfmmm_sampler_tape(bfmmm_sampler* s, const double* values, int64_t n) {
   if (!s) return sfail("null sampler");
+  if (s->dev.on) {                       // injected draws follow the reference's sequential call order: host path
+    if (dev_pull(s)) return 1;
+    s->dev.on = false;
+  }
   s->rng.use_tape = true;
   for (int64_t i = 0; i < n; i++) s->rng.tape.push_back(values[i]);
   return 0;
 }
+// positions the global random streams (keyed by seed, tick, purpose): the single bfmmm_host_update_* calls draw from
+// the stream of the current tick, so a caller iterating one update advances it between calls
+int bfmmm_sampler_set_tick(bfmmm_sampler* s, int64_t tick) {
+  if (!s) return sfail("null sampler");
+  s->tick = tick; s->rng.iteration = (uint64_t)tick;
+  return 0;
+}
 int64_t bfmmm_sampler_tape_left(bfmmm_sampler* s) { return s ? (int64_t)s->rng.tape.size() : -1; }
 int64_t bfmmm_sampler_iteration(bfmmm_sampler* s) { return s ? s->iteration : -1; }
-int64_t bfmmm_sampler_last_accept(bfmmm_sampler* s) { return s ? s->last_accept : -1; }
+int64_t bfmmm_sampler_last_accept(bfmmm_sampler* s) {
+  if (!s || dev_pull(s)) return -1;
+  return s->last_accept;
+}
 
 // ================================================================= host-side updates
+// The prior updates below run the statements of globals_core.cuh (shared with the device-resident sweep):
 // updatePi_PM (UpdatePi.h:84-116; lpdf_pi_PM :39-53 with sum_i log Z_ik from the device)
 int bfmmm_host_update_pi(bfmmm_sampler* s, const double* slz) {
-  const int K = s->K;
-  s->rng.open(HP_PI);
-  vecd al(K), prop(K), al2(K);
-  double sum = 0;
-  for (int k = 0; k < K; k++) {
-    al[k] = s->h.a_pi_PM * s->pi[k];
-    double sh = al[k] <= 0 ? 10.0 : al[k];              // rdirichlet guard, Distributions.h:24-28
-    prop[k] = s->rng.gamma(sh);
-    sum += prop[k];
-  }
-  for (int k = 0; k < K; k++) prop[k] /= sum;
-  auto lpdf = [&](const vecd& p) {
-    double l = 0;
-    vecd ap(K);
-    for (int k = 0; k < K; k++) {
-      l += (s->h.c[k] - 1) * std::log(p[k]);
-      l += (s->alpha3 * p[k] - 1) * slz[k];
-      ap[k] = s->alpha3 * p[k];
-    }
-    return l - (double)s->n_total * calc_lB(ap.data(), K);
-  };
-  auto propdens = [&](const vecd& x, const vecd& alpha) {
-    double dsum = 0;
-    for (int k = 0; k < K; k++) dsum += (alpha[k] - 1) * std::log(x[k]);
-    return dsum - calc_lB(alpha.data(), K);
-  };
-  double lnew = lpdf(prop), lold = lpdf(s->pi);
-  for (int k = 0; k < K; k++) al2[k] = s->h.a_pi_PM * prop[k];
-  double q_new = propdens(prop, al), q_old = propdens(s->pi, al2);
-  double acc = lnew - lold + q_old - q_new;
-  double u = s->rng.uniform();
-  if (std::log(u) < acc) s->pi = prop;
+  if (dev_begin_host_update(s)) return 1;
+  GlobalsView g = host_view(s);
+  HostRngAdapter r{&s->rng};
+  core_update_pi(g, r, slz);
   return tape_check(s);
 }
 
 // updateAlpha3 (UpdateAlpha3.h:36-63, lpdf_alpha3 :10-26)
 int bfmmm_host_update_alpha3(bfmmm_sampler* s, const double* slz) {
-  const int K = s->K;
-  s->rng.open(HP_ALPHA3);
-  const double sd = s->h.var_alpha3;
-  double prop = rtruncnorm_lo(s->alpha3, sd, 0.0, s->rng.uniform());
-  auto lpdf = [&](double a3, double a3_ph) {
-    double l = (-s->h.b) * a3;
-    vecd ap(K);
-    for (int k = 0; k < K; k++) { l += (a3 * s->pi[k] - 1) * slz[k]; ap[k] = a3 * s->pi[k]; }
-    l -= (double)s->n_total * calc_lB(ap.data(), K);
-    l += dtruncnorm_lo_log(a3_ph, a3_ph, sd, 0.0);      // as written in the reference (:23-24)
-    return l;
-  };
-  double lold = lpdf(s->alpha3, prop), lnew = lpdf(prop, s->alpha3);
-  double u = s->rng.uniform();
-  if (std::log(u) < lnew - lold) s->alpha3 = prop;
+  if (dev_begin_host_update(s)) return 1;
+  GlobalsView g = host_view(s);
+  HostRngAdapter r{&s->rng};
+  core_update_alpha3(g, r, slz);
   return tape_check(s);
 }
 
 // updateTau (UpdateTau.h:18-40) / updateTauMV (:47-68): note the integer division nu.n_cols / 2
 int bfmmm_host_update_tau(bfmmm_sampler* s) {
-  const int K = s->K, P = s->P;
-  s->rng.open(HP_TAU);
-  for (int k = 0; k < K; k++) {
-    double a = s->h.alpha_nu + (double)(P / 2);
-    double quad = 0;
-    for (int r = 0; r < P; r++) {
-      double pr = 0;
-      if (s->identity) pr = s->nu_(k, r);
-      else for (int c = std::max(0, r - s->hbP); c <= std::min(P - 1, r + s->hbP); c++) pr += s->Pmat[(size_t)r * P + c] * s->nu_(k, c);   // banded, symmetric
-      quad += s->nu_(k, r) * pr;
-    }
-    double b = s->h.beta_nu + 0.5 * quad;
-    double g = (1 / b) * s->rng.gamma(a);
-    s->tau[k] = s->identity ? 1 / g : g;
-  }
+  if (dev_begin_host_update(s)) return 1;
+  GlobalsView g = host_view(s);
+  HostRngAdapter r{&s->rng};
+  for (int k = 0; k < s->K; k++) core_update_tau_k(g, r, k);
   return tape_check(s);
 }
 
@@ -753,32 +1031,10 @@ int bfmmm_host_update_tau_eta(bfmmm_sampler* s) {
 
 // updateDelta (UpdateDelta.h:17-66): multiplicative gamma process shrinkage
 int bfmmm_host_update_delta(bfmmm_sampler* s) {
-  const int K = s->K, P = s->P, M = s->M;
-  s->rng.open(HP_DELTA);
-  for (int k = 0; k < K; k++)
-    for (int i = 0; i < M; i++) {
-      double p1, p2 = 1;
-      if (i == 0) {
-        p1 = s->A_(k, 0) + ((P * M) / 2.0);
-        for (int j = 0; j < P; j++) {
-          p2 += 0.5 * s->gamma_(k, j, 0) * std::pow(s->Phi_(k, j, 0), 2.0);
-          for (int m = 1; m < M; m++) {
-            double tt = 1;
-            for (int nn = 1; nn <= m; nn++) tt *= s->delta_(k, nn);
-            p2 += 0.5 * s->gamma_(k, j, m) * tt * std::pow(s->Phi_(k, j, m), 2.0);
-          }
-        }
-      } else {
-        p1 = s->A_(k, 1) + ((P * (M - i)) / 2.0);
-        for (int j = 0; j < P; j++)
-          for (int m = i; m < M; m++) {
-            double tt = 1;
-            for (int nn = 0; nn <= m; nn++) if (nn != i) tt *= s->delta_(k, nn);
-            p2 += 0.5 * s->gamma_(k, j, m) * tt * std::pow(s->Phi_(k, j, m), 2.0);
-          }
-      }
-      s->delta_(k, i) = (1 / p2) * s->rng.gamma(p1);
-    }
+  if (dev_begin_host_update(s)) return 1;
+  GlobalsView g = host_view(s);
+  HostRngAdapter r{&s->rng};
+  for (int k = 0; k < s->K; k++) core_update_delta_k(g, r, k);
   return tape_check(s);
 }
 
@@ -816,18 +1072,11 @@ int bfmmm_host_update_delta_xi(bfmmm_sampler* s) {
 
 // updateGamma (UpdateGamma.h:17-38)
 int bfmmm_host_update_gamma(bfmmm_sampler* s) {
-  const int K = s->K, P = s->P, M = s->M;
-  s->rng.open(HP_GAMMA);
-  const double nug = s->h.nu_1;
-  for (int i = 0; i < K; i++)
-    for (int l = 0; l < P; l++) {
-      double ph = 1;
-      for (int j = 0; j < M; j++) {
-        ph *= s->delta_(i, j);
-        double scale = 2 / (nug + ph * (s->Phi_(i, l, j) * s->Phi_(i, l, j)));
-        s->gamma_(i, l, j) = scale * s->rng.gamma((nug + 1) / 2);
-      }
-    }
+  if (dev_begin_host_update(s)) return 1;
+  GlobalsView g = host_view(s);
+  HostRngAdapter r{&s->rng};
+  for (int i = 0; i < s->K; i++)
+    for (int l = 0; l < s->P; l++) core_update_gamma_row(g, r, i, l);
   return tape_check(s);
 }
 
@@ -849,46 +1098,32 @@ int bfmmm_host_update_gamma_xi(bfmmm_sampler* s) {
   return tape_check(s);
 }
 
-static double lpdf_a1(double al, double be, double a, double delta) {          // UpdateA.h:17-23
-  return -std::log(std::tgamma(a)) + (a - 1) * std::log(delta) + (al - 1) * std::log(a) - (a * be);
-}
-static double lpdf_a2(double al, double be, double a, const double* delta, int M, int stride) {   // :33-44
-  double x = M - 1;
-  double l = -x * std::log(std::tgamma(a)) + (al - 1) * std::log(a) - (a * be);
-  for (int i = 1; i < M; i++) l += (a - 1) * std::log(delta[(size_t)i * stride]);
-  return l;
-}
-static void mh_a(bfmmm_sampler* s, double& a, bool first, const double* delta_row, int M, int stride) {
-  const bfmmm_hyper& h = s->h;
-  double sd = first ? h.var_epsilon1 / h.beta1l : h.var_epsilon2 / h.beta2l;
-  double cur = a;
-  double lp = first ? lpdf_a1(h.alpha1l, h.beta1l, cur, delta_row[0]) : lpdf_a2(h.alpha2l, h.beta2l, cur, delta_row, M, stride);
-  double prop = rtruncnorm_lo(cur, sd, 0.0, s->rng.uniform());
-  double lpn = first ? lpdf_a1(h.alpha1l, h.beta1l, prop, delta_row[0]) : lpdf_a2(h.alpha2l, h.beta2l, prop, delta_row, M, stride);
-  double acc = (lpn + dtruncnorm_lo_log(cur, prop, sd, 0.0)) - lp - dtruncnorm_lo_log(prop, cur, sd, 0.0);
-  double u = s->rng.uniform();
-  if (std::log(u) < acc) a = prop;
-}
-// updateA (UpdateA.h:58-135)
+// updateA (UpdateA.h:58-135; lpdf_a1 :17-23, lpdf_a2 :33-44 in globals_core.cuh)
 int bfmmm_host_update_A(bfmmm_sampler* s) {
-  s->rng.open(HP_A);
+  if (dev_begin_host_update(s)) return 1;
+  GlobalsView g = host_view(s);
+  HostRngAdapter r{&s->rng};
   for (int j = 0; j < s->K; j++)
-    for (int i = 0; i < 2; i++) mh_a(s, s->A_(j, i), i == 0, &s->delta_(j, 0), s->M, s->K);
+    for (int i = 0; i < 2; i++) core_update_A_one(g, r, j, i);
   return tape_check(s);
 }
 // updateAXi (UpdateA.h:137-209): order j, i, d
 int bfmmm_host_update_A_xi(bfmmm_sampler* s) {
-  s->rng.open(HP_A_XI);
+  HostRngAdapter r{&s->rng};
   for (int j = 0; j < s->K; j++)
     for (int i = 0; i < 2; i++)
-      for (int d = 0; d < s->D; d++) mh_a(s, s->A_xi_(j, i, d), i == 0, &s->delta_xi_(j, 0, d), s->M, s->K);
+      for (int d = 0; d < s->D; d++) {
+        auto st = r.open(HP_A_XI, (uint64_t)(j * 2 + i) * bf::DMAX + d);
+        core_mh_a(s->h, st, s->A_xi_(j, i, d), i == 0, &s->delta_xi_(j, 0, d), s->M, s->K);
+      }
   return tape_check(s);
 }
 
 // updatePhi (UpdatePhi.h:23-89): blocks (j, m), prior diag(tilde_tau(j,m) * gamma(j,.,m))
 int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  if (dev_begin_host_update(s)) return 1;
   const int K = s->K, P = s->P, M = s->M;
-  if (!s->zpre_on) s->rng.open(HP_PHI);
+  s->blk_purpose = HP_PHI; s->blk_index = 0;
   vecd diag(P);
   if (!s->ragged && P >= PREFACTOR_MIN_P) {
     std::vector<PreBlock> blocks;
@@ -918,8 +1153,9 @@ int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtY
 }
 // updateNu (UpdateNu.h:24-74): blocks j, prior tau_j * P (MV: (1/tau_j) I, :195-196)
 int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  if (dev_begin_host_update(s)) return 1;
   const int K = s->K, P = s->P;
-  if (!s->zpre_on) s->rng.open(HP_NU);
+  s->blk_purpose = HP_NU; s->blk_index = 0;
   vecd diag(P);
   const bool pre = !s->ragged && P >= PREFACTOR_MIN_P;
   std::vector<vecd>& priors = s->pre_prior;            // persistent: no 1.3 MB allocations per sweep
@@ -958,8 +1194,9 @@ int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW
 }
 // updateEta (UpdateEta.h:28-94): d outer, j inner; prior tau_eta(j,d) * P (MV: (1/tau_eta) I)
 int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  if (dev_begin_host_update(s)) return 1;
   const int K = s->K, P = s->P, D = s->D;
-  s->rng.open(HP_ETA);
+  s->blk_purpose = HP_ETA; s->blk_index = 0;
   vecd& prior = s->prior_buf;
   if (prior.size() < (size_t)P * P) prior.assign((size_t)P * P, 0.0);
   vecd diag(P);
@@ -977,8 +1214,9 @@ int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtY
 }
 // updateXiCovariateAdj (UpdateXi.h:26-93): order j, m, d; prior diag(tilde_tau_xi(j,m,d) * gamma_xi_j(.,d,m))
 int bfmmm_host_update_xi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
+  if (dev_begin_host_update(s)) return 1;
   const int K = s->K, P = s->P, M = s->M, D = s->D;
-  s->rng.open(HP_XI);
+  s->blk_purpose = HP_XI; s->blk_index = 0;
   vecd diag(P);
   for (int j = 0; j < K; j++)
     for (int m = 0; m < M; m++)
@@ -993,6 +1231,7 @@ int bfmmm_host_update_xi(bfmmm_sampler* s, const double* WtW, const double* BtYW
 
 // updateSigma's draw (UpdateSigma.h:47-53; tempered :98-107; MV :149-151)
 int bfmmm_host_update_sigma(bfmmm_sampler* s, double ssr, double beta, int tempered) {
+  if (dev_begin_host_update(s)) return 1;
   s->rng.open(HP_SIGMA);
   double a, b1;
   if (tempered) { a = (beta * s->n_points_total) / 2 + s->h.alpha_0; b1 = (beta / 2) * ssr + s->h.beta_0; }
@@ -1074,13 +1313,17 @@ static int record_iteration(bfmmm_sampler* s) {
   return 0;
 }
 
+}  // extern "C"
+namespace { int record_iteration_fwd(bfmmm_sampler* s) { return record_iteration(s); } }
+extern "C" {
+
 // ================================================================= driver loops
 static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta);
 int bfmmm_sampler_step(bfmmm_sampler* s, int sweep, double beta) {
   if (!s) return sfail("null sampler");
   if (!s->e) return sfail("bfmmm_sampler_step: detached sampler has no engine");
   const double t0 = now_s(), w0 = s->t_wait, p0 = s->t_push;
-  int rc = sampler_step_impl(s, sweep, beta);
+  int rc = s->dev.on ? sampler_step_device(s, sweep, beta) : sampler_step_impl(s, sweep, beta);
   s->t_host += (now_s() - t0) - (s->t_wait - w0) - (s->t_push - p0);
   if (s->rng.tape_underrun) { s->rng.tape_underrun = false; if (!rc) rc = sfail("bfmmm_sampler_step: the tape of injected draws ran out during the sweep"); }
   return rc;
@@ -1111,8 +1354,15 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   // While the device runs the Z and statistics kernels: the standard normals of the Phi and nu block draws
   // (they do not depend on the statistics), from the streams and in the order the draws would use.
   s->zpre.clear(); s->zpre_pos = 0;
-  if (do_phi) { s->rng.open(HP_PHI); for (int i = 0; i < s->K * s->M * s->P; i++) s->zpre.push_back(s->rng.normal()); }
-  if (do_nu) { s->rng.open(HP_NU); for (int i = 0; i < s->K * s->P; i++) s->zpre.push_back(s->rng.normal()); }
+  if (!s->rng.use_tape) {
+    HostRngAdapter r{&s->rng};
+    for (int upd = 0; upd < 2; upd++) {
+      if (upd == 0 ? !do_phi : !do_nu) continue;
+      const int nblk = upd == 0 ? s->K * s->M : s->K;
+      for (int t = 0; t < nblk; t++)
+        for (int p = 0; p < s->P; p++) { auto st = r.open(upd == 0 ? HP_PHI : HP_NU, ((uint64_t)t << 12) + (uint64_t)p); s->zpre.push_back(st.normal()); }
+    }
+  }
   if (reduce_and_read(s)) return 1;
   if (s->ll_pending) {                                     // previous sweep's post-chi SSR arrived with this exchange
     s->last_ssr = st_ssr_after(s);
@@ -1127,7 +1377,7 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   // Philox stream and reads exactly what it reads in the reference's order (Phi uses the previous
   // delta/gamma, nu the previous tau; delta, A, gamma see the new Phi; tau the new nu), so the chain is
   // the one of BFMMM.h:1500-1554 -- only wall-clock placement differs.
-  s->zpre_on = true;
+  s->zpre_on = !s->rng.use_tape;
   int rc_blocks = (do_phi && bfmmm_host_update_phi(s, st_wtw(s), st_btyw(s), beta)) ||   // updatePhi
                   (do_nu && bfmmm_host_update_nu(s, st_wtw(s), st_btyw(s), beta));        // updateNu
   s->zpre_on = false;
@@ -1231,6 +1481,7 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
   const double geom = std::pow(beta_N_t, 1.0 / N_t);
   for (int i = 1; i < N_t; i++) ladder[i] = ladder[i - 1] * geom;      // as written at BFMMM.h:1453-1460
   const int m = 2 * N_t;
+  if (dev_pull(s)) return 1;
   if (flush_loglik(s)) return 1;
   // slot 0: the current state.  Its SSR: one data pass with the current globals.
   if (push_globals(s)) return 1;
@@ -1247,6 +1498,7 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
       // a failed rung leaves nothing half-advanced: globals and (Z, chi) go back to the pre-transition state
       s->in_tt = false;
       restore_params(s, saved);
+      s->dev.dev_stale = true; s->dev.host_stale = false;
       bfmmm_state_restore(s->e);
       return 1;
     }
@@ -1272,7 +1524,9 @@ int bfmmm_sampler_tempered_transition(bfmmm_sampler* s, int N_t, double beta_N_t
   if (ok) s->tt_accepts++;
   else {
     // restore the pre-transition parameters; the bookkeeping (tick, counters, traces, random streams) moves on
+    if (dev_pull(s)) return 1;
     restore_params(s, saved);
+    s->dev.dev_stale = true;
     if (bfmmm_state_restore(s->e)) return 1;
   }
   if (s->rec.on && record_iteration(s)) return 1;

@@ -300,13 +300,14 @@ static __device__ __noinline__ double stirling_corr_diff_small(double x, double 
 // `ok` is cleared otherwise and the caller evaluates the reference's formula as written).
 template <int K>
 __device__ __forceinline__ double z_logratio_closed(const double (&sh)[K], const double (&r)[K], const double (&zp)[K],
-                                                    const double (&dl)[K], const PassArgs& a, bool& ok) {
+                                                    const double (&dl)[K], const PassArgs& a, const double* par, bool& ok) {
   double acc = 0, tot = 0, tots = 0;
+  const double alpha3 = par[8];
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const double shp = a.a_Z_PM * zp[k];
     const double rp = fast_rcp1(shp);
-    acc = fma(fma(a.alpha3, a.pi[k], 0.5) - (sh[k] + shp), dl[k], acc);
+    acc = fma(fma(alpha3, par[k], 0.5) - (sh[k] + shp), dl[k], acc);
     double ds = stirling_corr(rp) - stirling_corr(r[k]);
     if (shp < 16.0 || sh[k] < 16.0) ds = stirling_corr_diff_small(sh[k], r[k], shp, rp);
     acc -= ds;
@@ -360,12 +361,16 @@ __device__ __forceinline__ unsigned z_candidate_round(const PassArgs& a, uint64_
 template <int K, int M, bool COV, int V, bool RG>
 __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
+  // pi, alpha_3, sigma^2: kernel arguments, or device memory when the sweep's small updates run on the device
+  __shared__ double s_par[10];
+  if (threadIdx.x < 10)
+    s_par[threadIdx.x] = a.zpar_dev ? a.zpar_dev[threadIdx.x] : (threadIdx.x < 8 ? a.pi[threadIdx.x] : (threadIdx.x == 8 ? a.alpha3 : a.sigma_sq));
   build_log_table();
   stage_globals(a, g);
   double red[K + 1];
 #pragma unroll
   for (int j = 0; j <= K; j++) red[j] = 0;
-  const double hb = a.beta / (2 * a.sigma_sq);
+  const double hb = a.beta / (2 * s_par[9]);
   // persistent blocks: every thread walks the functions with a grid stride, one reduction per block
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
     FnState<K, M, COV, V> st;
@@ -461,12 +466,12 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
         rr[k] = fast_rcp(closed ? sh[k] : 1.0);
         dl[k] = fast_log_pos(closed ? zp[v][k] * (a.a_Z_PM * rr[k]) : 1.0);      // log(z*_k / z_k)
       }
-      lr[v] = z_logratio_closed<K>(sh, rr, zp[v], dl, a, closed);
+      lr[v] = z_logratio_closed<K>(sh, rr, zp[v], dl, a, s_par, closed);
       if (!closed) {
         double tz[K], tzp[K], tpi[K];
 #pragma unroll
-        for (int k = 0; k < K; k++) { tz[k] = st.z[v][k]; tzp[k] = zp[v][k]; tpi[k] = a.pi[k]; }
-        lr[v] = z_logratio_exact<K>(tz, tzp, tpi, a.alpha3, a.a_Z_PM);
+        for (int k = 0; k < K; k++) { tz[k] = st.z[v][k]; tzp[k] = zp[v][k]; tpi[k] = s_par[k]; }
+        lr[v] = z_logratio_exact<K>(tz, tzp, tpi, s_par[8], a.a_Z_PM);
       }
       lu[v] = fast_log(uacc);
     }
@@ -944,7 +949,8 @@ inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extr
     per_sm = it->second.second;
   }
   int need = pass_grid(a.ld, V);
-  int grid = a.sm_count * per_sm;
+  int grid = a.sm_count * per_sm - a.grid_reserve;
+  if (grid < 1) grid = 1;
   if (grid > need) grid = need;
   if (grid > a.max_blocks) grid = a.max_blocks;
   kern<<<grid, PF_THREADS, smem, s>>>(a);

@@ -237,6 +237,15 @@ class Sampler:
         v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).ravel())
         self._chk(self._lib.bfmmm_sampler_tape(self._h, _p(v), C.c_int64(v.size)))
 
+    @property
+    def device_resident(self) -> bool:
+        """True when the sweeps run without a host round trip (globals drawn by device kernels)."""
+        return bool(self._lib.bfmmm_sampler_device_resident(self._h))
+
+    def set_tick(self, tick: int):
+        """positions the random streams of the host_update calls that follow"""
+        self._chk(self._lib.bfmmm_sampler_set_tick(self._h, C.c_int64(tick)))
+
     def tape_left(self):
         self._lib.bfmmm_sampler_tape_left.restype = C.c_int64
         return int(self._lib.bfmmm_sampler_tape_left(self._h))

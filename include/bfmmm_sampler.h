@@ -58,6 +58,12 @@ int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int
                                   const double* G, double sum_half_total, double n_points_total, uint64_t seed,
                                   bfmmm_sampler** out);
 void bfmmm_sampler_destroy(bfmmm_sampler* s);
+/* 1 when the sweeps run device-resident: common basis (functional or multivariate) without covariates, no injected
+ * draws, and block precisions small enough for one thread block; the global parameters then live in device memory,
+ * every update of the sweep is a kernel (csrc/globals_kernels.cu) and the host only reads on demand.  Selected with
+ * the environment variable BFMMM_DEVICE_GLOBALS=1 when the sampler is created (default: the host draws the globals,
+ * which is faster on one GPU: DESIGN.md section 4). */
+int bfmmm_sampler_device_resident(bfmmm_sampler* s);
 int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx);
 /* Native NCCL hook (csrc/nccl_hook.cu): ncclAllReduce on the engine's stream, no host-language round trip.
  * libnccl is dlopen'ed (libnccl_path, or the library already mapped into the process when NULL).  Rank 0
@@ -121,6 +127,9 @@ int64_t bfmmm_sampler_iteration(bfmmm_sampler* s);
 /* acceptance count of the last Z step (summed over shards) */
 int64_t bfmmm_sampler_last_accept(bfmmm_sampler* s);
 
+/* positions the global random streams (seed, tick, purpose) used by the bfmmm_host_update_* calls that follow;
+ * bfmmm_sampler_step advances the tick itself */
+int bfmmm_sampler_set_tick(bfmmm_sampler* s, int64_t tick);
 /* injected draws for the parity tests: values are consumed in the reference's call order */
 int bfmmm_sampler_tape(bfmmm_sampler* s, const double* values, int64_t n);
 int64_t bfmmm_sampler_tape_left(bfmmm_sampler* s);

@@ -129,6 +129,29 @@ def read_arma_txt(path):
     raise ValueError(head)
 
 
+def read_arma_field_cube_bin(path):
+    """ARMA_FLD_BIN field of cubes (Phi0.txt: 150 x 1 field of K x P x M cubes): list of column-major cubes."""
+    raw = open(path, "rb").read()
+    pos = 0
+
+    def line():
+        nonlocal pos
+        e = raw.index(b"\n", pos)
+        out = raw[pos:e].decode()
+        pos = e + 1
+        return out
+    assert line() == "ARMA_FLD_BIN"
+    nr, nc = int(line()), int(line())
+    cubes = []
+    for _ in range(nr * nc):
+        assert line() == "ARMA_CUB_BIN_FN008"
+        r, c, sl = (int(x) for x in line().split())
+        v = np.frombuffer(raw, dtype="<f8", count=r * c * sl, offset=pos)
+        pos += 8 * r * c * sl
+        cubes.append(v.reshape(sl, c, r).transpose(2, 1, 0).copy())       # [r][c][slice]
+    return cubes
+
+
 def main():
     if not os.path.isdir(TD):
         sys.exit(f"{TD} not found: run this in the build container")
@@ -163,6 +186,22 @@ def main():
         summ[fam + "_nu_med"] = np.median(nu[:, :, half], axis=2)
         summ[fam + "_Z_med"] = np.median(Z[:, :, half], axis=2)
         summ[fam + "_sigma_chain"] = sig
+        # Posterior summaries of the second half of the stored chain (75 draws).  Z, nu, Phi are only identified up to
+        # the mixing transformations Z -> Z A, nu -> A^-1 nu (labels, rotations of the pseudo-eigenfunctions), so the
+        # comparable quantities are the function-level ones: the fitted mean coefficients (Z nu)_i (n x P) and the
+        # pointwise variances diag(U_i U_i'), U_i = sum_k Z_ik Phi_k (n x P); Z, nu and sum_m phi_km phi_km' are kept
+        # with the labels as stored.  Mean, sd and 5 / 95 % quantiles over the draws.
+        Phi = read_arma_field_cube_bin(os.path.join(d, "Phi0.txt"))
+        idx = range(len(sig) // 2, len(sig))
+        fit = np.stack([Z[:, :, i] @ nu[:, :, i] for i in idx])
+        cov = np.stack([np.einsum("kpm,kqm->kpq", Phi[i], Phi[i]) for i in idx])
+        fvar = np.stack([(np.einsum("nk,kpm->npm", Z[:, :, i], Phi[i]) ** 2).sum(axis=2) for i in idx])
+        for name, arr in (("fit", fit), ("fvar", fvar), ("cov", cov), ("Z", np.stack([Z[:, :, i] for i in idx])),
+                          ("nu", np.stack([nu[:, :, i] for i in idx]))):
+            summ[f"{fam}_{name}_mean"] = arr.mean(axis=0)
+            summ[f"{fam}_{name}_q05"] = np.quantile(arr, 0.05, axis=0)
+            summ[f"{fam}_{name}_q95"] = np.quantile(arr, 0.95, axis=0)
+            summ[f"{fam}_{name}_sd"] = arr.std(axis=0, ddof=1)
     np.savez_compressed(os.path.join(OUT, "trace_summaries.npz"), **summ)
     print("wrote golden fixtures to", OUT)
 

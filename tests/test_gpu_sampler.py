@@ -26,6 +26,41 @@ def _functional(seed=5, n=300, T=60, K=2, P=8, M=2, sigma_sq=0.01):
     return s, eng, smp
 
 
+def _chain_summaries(eng, smp, sweeps, burn, every=5):
+    """Runs the full sweep and keeps, after burn-in, sigma^2 and the identified function-level quantities of every
+    `every`-th draw: the fitted mean coefficients (Z nu)_i and the pointwise variances diag(U_i U_i'), U_i = sum_k Z_ik Phi_k."""
+    sig, fit, fvar = [], [], []
+    for it in range(sweeps):
+        smp.step(bf.SWEEP_FULL)
+        g = smp.get()
+        sig.append(g["sigma_sq"])
+        if it >= burn and (it - burn) % every == 0:
+            Z, _ = eng.get_state(chi=False)
+            fit.append(Z @ g["nu"])
+            fvar.append((np.einsum("nk,kpm->npm", Z, g["Phi"]) ** 2).sum(axis=2))
+    return np.array(sig), np.array(fit), np.array(fvar)
+
+
+def _assert_posterior_agrees(S, fam, fit, fvar, ess_ref=8.0, ess_ours=25.0):
+    """Posterior means and 5-95 % credible intervals of the identified quantities against the reference's stored chain
+    (second half of inst/test-data/<fam>_trace: 75 autocorrelated draws), within Monte-Carlo error: the standardised
+    difference of the means uses the two chains' posterior sds and conservative effective sample sizes (the
+    reference's 75 draws count as 8 independent ones, ours as 25)."""
+    out = {}
+    for name, ours in (("fit", fit), ("fvar", fvar)):
+        m_ref, sd_ref = S[f"{fam}_{name}_mean"], S[f"{fam}_{name}_sd"]
+        m, sd = ours.mean(axis=0), ours.std(axis=0, ddof=1)
+        z = np.abs(m - m_ref) / np.sqrt(sd_ref ** 2 / ess_ref + sd ** 2 / ess_ours + 1e-300)
+        w_ref = S[f"{fam}_{name}_q95"] - S[f"{fam}_{name}_q05"]
+        w = np.quantile(ours, 0.95, axis=0) - np.quantile(ours, 0.05, axis=0)
+        out[name] = (float(np.median(z)), float(np.quantile(z, 0.95)), float(np.median(w / w_ref)))
+    print(fam, "posterior agreement (median z, 95 % z, median interval-width ratio):", out)
+    for name, (zmed, z95, wr) in out.items():
+        assert zmed < 1.5 and z95 < 5.0, (fam, name, out)          # means agree within Monte-Carlo error
+        assert 0.4 < wr < 2.5, (fam, name, out)                    # credible intervals of comparable width
+    return out
+
+
 def test_full_sweep_recovers_sigma_and_memberships():
     s, eng, smp = _functional()
     sig, acc = [], []
@@ -165,13 +200,12 @@ def test_config1_sigma_matches_reference_stored_chain():
     eng.set_state(Zref, rng.normal(size=(n, M)))
     smp = bf.Sampler(eng, hyper=bf.default_hyper(True), n_total=n, Pmat=orc.pmat_rw1(P), seed=5)
     smp.set(nu=S["Functional_nu_med"], Phi=0.1 * rng.normal(size=(K, P, M)), sigma_sq=1.0, pi=S["Functional_pi_med"], alpha3=1.0)
-    sig = []
-    for _ in range(3000):
-        smp.step(bf.SWEEP_FULL)
-        sig.append(smp.get()["sigma_sq"])
+    sig, fit, fvar = _chain_summaries(eng, smp, 3000, 1500)
     med = np.median(sig[1500:])
     lo, mid, hi = S["Functional_sigma_q"]
     assert lo * 0.9 < med < hi * 1.1, (med, lo, hi)
+    # nu, Phi, Z: posterior means and credible intervals of the identified quantities vs Nu0 / Phi0 / Z0.txt
+    _assert_posterior_agrees(S, "Functional", fit, fvar)
     smp.close(); eng.close()
 
 
@@ -249,13 +283,11 @@ def test_high_dimensional_functional_matches_reference_stored_chain():
     smp = bf.Sampler(eng, hyper=bf.default_hyper(True), n_total=n, Pmat=Pm, seed=6)
     smp.set(nu=S["HDFunctional_nu_med"], Phi=0.1 * rng.normal(size=(K, P, M)), sigma_sq=1.0,
             pi=S["HDFunctional_pi_med"], alpha3=1.0)
-    sig = []
-    for _ in range(3000):
-        smp.step(bf.SWEEP_FULL)
-        sig.append(smp.get()["sigma_sq"])
+    sig, fit, fvar = _chain_summaries(eng, smp, 3000, 1500)
     med = np.median(sig[1500:])
     lo, mid, hi = S["HDFunctional_sigma_q"]
     assert lo * 0.85 < med < hi * 1.15, (med, lo, hi)
+    _assert_posterior_agrees(S, "HDFunctional", fit, fvar)
     smp.close(); eng.close()
 
 
@@ -272,38 +304,67 @@ def test_multivariate_matches_reference_stored_chain():
     smp = bf.Sampler(eng, hyper=bf.default_hyper(True), n_total=n, seed=8)
     smp.set(nu=S["Multivariate_nu_med"], Phi=0.1 * rng.normal(size=(K, R, M)), sigma_sq=1.0,
             pi=S["Multivariate_pi_med"], alpha3=1.0)
-    sig = []
-    for _ in range(4000):
-        smp.step(bf.SWEEP_FULL)
-        sig.append(smp.get()["sigma_sq"])
+    sig, fit, fvar = _chain_summaries(eng, smp, 4000, 2000)
     med = np.median(sig[2000:])
     lo, mid, hi = S["Multivariate_sigma_q"]
     assert lo * 0.6 < med < hi * 1.6, (med, lo, hi)     # n*R = 200 observations: a wide posterior
+    _assert_posterior_agrees(S, "Multivariate", fit, fvar)
     smp.close(); eng.close()
 
 
-def test_device_sigma_draw_is_the_host_draw():
-    """The fused path draws sigma^2 on the device behind the SSR pass (bfmmm_sigma_draw_async) from the stream and
-    sampler of the host draw: the two chains coincide (libdevice vs libm rounding only)."""
-    out = {}
-    for mode in ("fused", "host"):
-        if mode == "host":
-            os.environ["BFMMM_NO_FUSED_SIGMA"] = "1"
-        try:
+def _chain(mode, sweeps, sweep_kind=None, mv=False):
+    """A short chain with the globals drawn on the device (device-resident sweep) or on the host."""
+    env = {"host": {}, "host_fused_sigma": {}, "host_plain": {"BFMMM_NO_FUSED_SIGMA": "1"},
+           "device": {"BFMMM_DEVICE_GLOBALS": "1"}}[mode]
+    os.environ.update(env)
+    try:
+        if mv:
+            s = synth.multivariate(seed=9, n=500, R=12, K=3, M=2, sigma_sq=0.02)
+            eng = bf.Engine(model=MULTIVARIATE, n=500, K=3, P=12, M=2, y=s["y"])
+            eng.set_state(s["Z"], s["chi"])
+            smp = bf.Sampler(eng, hyper=bf.default_hyper(True, a_Z_PM=2000.0), n_total=500, seed=11)
+            smp.set(nu=s["par"]["nu"], Phi=s["par"]["Phi"], sigma_sq=0.02, pi=s["pi"], alpha3=1.0)
+        else:
             s, eng, smp = _functional(seed=9, n=500)
-            chain = []
-            for _ in range(5):
-                smp.step(bf.SWEEP_FULL)
-                g = smp.get()
-                chain.append([g["sigma_sq"], g["loglik"], *g["nu"].ravel(), *g["pi"]])
-            Z, chi = eng.get_state()
-            out[mode] = (np.array(chain), Z, chi)
-            smp.close(); eng.close()
-        finally:
-            os.environ.pop("BFMMM_NO_FUSED_SIGMA", None)
-    a, b = out["fused"], out["host"]
-    assert np.max(np.abs(a[0][0] - b[0][0]) / np.abs(b[0][0])) < 1e-12      # first sweep: identical up to rounding
-    assert np.max(np.abs(a[0] - b[0]) / (1e-3 + np.abs(b[0]))) < 1e-6        # five sweeps later still the same chain
+        assert smp.device_resident == (mode == "device")
+        chain = []
+        for _ in range(sweeps):
+            smp.step(bf.SWEEP_FULL if sweep_kind is None else sweep_kind)
+            g = smp.get()
+            chain.append(np.concatenate([[g["sigma_sq"], g["loglik"], g["alpha3"]], g["nu"].ravel(), g["Phi"].ravel(), g["pi"],
+                                         g["delta"].ravel(), g["gamma"].ravel(), g["A"].ravel(), g["tau"]]))
+        Z, chi = eng.get_state()
+        acc = smp.last_accept
+        smp.close(); eng.close()
+        return np.array(chain), Z, chi, acc
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("mv", [False, True])
+@pytest.mark.parametrize("kind", [bf.SWEEP_FULL, bf.SWEEP_THETA, bf.SWEEP_NU_Z])
+def test_device_resident_sweep_is_the_host_sweep(kind, mv):
+    """The device-resident sweep (Gaussian block draws, sigma^2, pi, alpha_3, delta, A, gamma, tau drawn by
+    csrc/globals_kernels.cu) runs the statements and the Philox streams of the host loop (csrc/globals_core.cuh): after
+    one sweep every global parameter, Z and chi coincide up to libm / libdevice rounding; a few sweeps later the two
+    are still the same chain."""
+    a = _chain("device", 4, kind, mv)
+    b = _chain("host", 4, kind, mv)
+    scale = 1e-3 + np.abs(b[0])
+    assert np.max(np.abs(a[0][0] - b[0][0]) / scale[0]) < 1e-9, np.argmax(np.abs(a[0][0] - b[0][0]) / scale[0])
+    assert a[3] == b[3] or abs(a[3] - b[3]) <= 2                                  # accepted proposals of the last Z step
+    assert np.mean(np.abs(a[0] - b[0]) / scale < 1e-5) > 0.99                      # four sweeps later: still the same chain
+    assert np.mean(np.all(np.abs(a[1] - b[1]) < 1e-8, axis=1)) > 0.99
+    assert np.mean(np.all(np.abs(a[2] - b[2]) < 1e-6, axis=1)) > 0.99
+
+
+def test_device_sigma_draw_is_the_host_draw():
+    """Host-drawn globals: the fused path draws sigma^2 on the device behind the SSR pass (bfmmm_sigma_draw_async) from
+    the stream and sampler of the host draw: the two chains coincide (libdevice vs libm rounding only)."""
+    a, b = _chain("host_fused_sigma", 5), _chain("host_plain", 5)
+    assert np.max(np.abs(a[0][0] - b[0][0]) / (1e-3 + np.abs(b[0][0]))) < 1e-10      # first sweep: identical up to rounding
+    assert np.max(np.abs(a[0] - b[0]) / (1e-3 + np.abs(b[0]))) < 1e-6                 # five sweeps later still the same chain
     assert np.mean(np.all(np.abs(a[1] - b[1]) < 1e-9, axis=1)) > 0.99
 
 

@@ -36,6 +36,9 @@ def _worker(rank, world, port, q, n_sweeps, hook="python"):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if hook.endswith("_dev"):       # device-resident sweep: the exchanges are queued on the stream, no host read-back
+        os.environ["BFMMM_DEVICE_GLOBALS"] = "1"
+        hook = hook[:-4]
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     bf, eng, smp, lo, hi = _setup(rank, world)
@@ -80,7 +83,7 @@ def _worker(rank, world, port, q, n_sweeps, hook="python"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("hook", ["python", "nccl", "p2p"])
+@pytest.mark.parametrize("hook", ["python", "nccl", "p2p", "nccl_dev", "p2p_dev"])
 def test_two_gpu_chain_follows_single_gpu_chain(hook):
     import torch
     if torch.cuda.device_count() < 2:
