@@ -41,6 +41,8 @@ EXPORTS = [
     "bfmmm_host_update_gamma", "bfmmm_host_update_A", "bfmmm_host_update_tau_eta", "bfmmm_host_update_delta_xi",
     "bfmmm_host_update_gamma_xi", "bfmmm_host_update_A_xi", "bfmmm_host_update_phi", "bfmmm_host_update_nu",
     "bfmmm_host_update_eta", "bfmmm_host_update_xi", "bfmmm_host_update_sigma",
+    # include/bfmmm_post.h
+    "bfmmm_quantiles",
     "bfmmm_debug_enable_acc", "bfmmm_debug_get_acc", "bfmmm_debug_update_z_rng", "bfmmm_debug_update_chi_rng",
     "bfmmm_debug_get_cache", "bfmmm_debug_fastmath",
 ]

@@ -39,6 +39,7 @@ namespace bf {
 constexpr int DB_THREADS = 384;
 constexpr int DB_WARPS = DB_THREADS / 32;
 constexpr int DB_PMAX = 32;             // coefficients per block with a banded (non-diagonal) precision
+constexpr int DB_PITCH = 33;
 
 __global__ void __launch_bounds__(DB_THREADS) draw_blocks_kernel(const DrawArgs a) {
   extern __shared__ double sm[];
@@ -55,9 +56,8 @@ __global__ void __launch_bounds__(DB_THREADS) draw_blocks_kernel(const DrawArgs 
   double* Ub = H + (size_t)nb * P;         // nb x (P * ldb) band of Prec_a, then of U_a
   double* rd = Ub + (size_t)nb * P * ldb;  // nb x P  1 / U_a[i][i]
   double* Gs = rd + (size_t)nb * P;        // P x P basis Gram (banded precisions only)
-  double* Cv = Gs + (diag ? 0 : P * P);    // nb x P x 32  work columns of the solves
-  double* T = Cv + (diag ? 0 : (size_t)nb * P * 32);  // nb x P x 32  T_a, row i at T + (a P + i) 32
-  if ((T - sm) & 1) T++;                   // rows are read as double2
+  double* Cv = Gs + (diag ? 0 : P * P);    // nb x P x DB_PITCH  columns of the solves: T_a[i][k] at (a P + i) DB_PITCH + k
+                                           // (odd pitch: lanes = columns while solving, lanes = rows in the chain, both conflict-free)
   __shared__ int s_fail;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_fail = 0;
@@ -169,22 +169,24 @@ __global__ void __launch_bounds__(DB_THREADS) draw_blocks_kernel(const DrawArgs 
       if (bad) s_fail = 1;
       // D: lane k < P solves  U U' y = sc G[:, k]  -> column k of T_a = sc Prec_a^-1 G;  lane P solves
       // U U' y = sc (B'Y'W)_a  -> the mean part of h_a;  lane 31 the forward solve  U' x = z  (= chol_lower(Cov_a) z)
-      double* Y = Cv + (size_t)t * P * 32;            // work columns, Y[i * 32 + lane]
+      double* Y = Cv + (size_t)t * P * DB_PITCH;      // Y[i * DB_PITCH + lane]
+      for (int i = 0; i < P; i++) Y[i * DB_PITCH + lane] = 0.0;      // columns beyond P + 1 stay zero (the chain reads 32)
+      __syncwarp();
       if (lane <= P) {
         const int c = lane;
         for (int i = P - 1; i >= 0; i--) {            // U w = b
           double s = sc * (c < P ? Gs[c * P + i] : R[f * P + i]);
           const int k1 = i + hb < P - 1 ? i + hb : P - 1;
-          for (int k = i + 1; k <= k1; k++) s = fma(-A[i * ldb + (k - i)], Y[k * 32 + c], s);
-          Y[i * 32 + c] = s * r[i];
+#pragma unroll 4
+          for (int k = i + 1; k <= k1; k++) s = fma(-A[i * ldb + (k - i)], Y[k * DB_PITCH + c], s);
+          Y[i * DB_PITCH + c] = s * r[i];
         }
         for (int i = 0; i < P; i++) {                 // U' y = w, in place
-          double s = Y[i * 32 + c];
+          double s = Y[i * DB_PITCH + c];
           const int k0 = i - hb > 0 ? i - hb : 0;
-          for (int k = k0; k < i; k++) s = fma(-A[k * ldb + (i - k)], Y[k * 32 + c], s);
-          s *= r[i];
-          Y[i * 32 + c] = s;
-          if (c < P) T[((size_t)t * P + i) * DB_PMAX + c] = s;
+#pragma unroll 4
+          for (int k = k0; k < i; k++) s = fma(-A[k * ldb + (i - k)], Y[k * DB_PITCH + c], s);
+          Y[i * DB_PITCH + c] = s * r[i];
         }
       }
       if (lane == 31) {                               // U' x = z
@@ -198,11 +200,8 @@ __global__ void __launch_bounds__(DB_THREADS) draw_blocks_kernel(const DrawArgs 
         }
       }
       __syncwarp();
-      // h_a = mean part + U^-T z;  the columns of T_a beyond P are zero
-      if (lane < P) {
-        H[(size_t)t * P + lane] += Y[lane * 32 + P];
-        for (int k = P; k < DB_PMAX; k++) T[((size_t)t * P + lane) * DB_PMAX + k] = 0.0;
-      }
+      // h_a = mean part (column P of the solves) + U^-T z
+      if (lane < P) H[(size_t)t * P + lane] += Y[lane * DB_PITCH + P];
     }
     __syncthreads();
   }
@@ -233,14 +232,14 @@ __global__ void __launch_bounds__(DB_THREADS) draw_blocks_kernel(const DrawArgs 
       } else {
         // row `lane` of T_a into registers (rows >= P are never read: their lanes idle), v around by shuffles
         double trow[DB_PMAX];
-        const double* Ti = T + ((size_t)t * P + (lane < P ? lane : 0)) * DB_PMAX;
+        const double* Ti = Cv + ((size_t)t * P + (lane < P ? lane : 0)) * DB_PITCH;
 #pragma unroll
-        for (int k = 0; k < DB_PMAX; k += 2) { const double2 u = *reinterpret_cast<const double2*>(Ti + k); trow[k] = u.x; trow[k + 1] = u.y; }
+        for (int k = 0; k < DB_PMAX; k++) trow[k] = Ti[k];
         const double cold = lane < P ? C[f * P + lane] : 0.0;
         const double v = lane < P ? fma(-saa, cold, Mt[f * P + lane]) : 0.0;
         double x4[4] = {lane < P ? H[(size_t)t * P + lane] : 0.0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < DB_PMAX; k++) x4[k & 3] = fma(-trow[k], __shfl_sync(0xffffffffu, v, k), x4[k & 3]);     // T rows are zero beyond P
+        for (int k = 0; k < DB_PMAX; k++) x4[k & 3] = fma(-trow[k], __shfl_sync(0xffffffffu, v, k), x4[k & 3]);     // v is zero on the lanes beyond P
         const double x = (x4[0] + x4[1]) + (x4[2] + x4[3]);
         if (lane < P) {
           const double dl = x - cold;
@@ -280,7 +279,7 @@ __global__ void __launch_bounds__(DB_THREADS) draw_blocks_kernel(const DrawArgs 
 size_t draw_blocks_smem(const DrawArgs& a) {
   const size_t K = a.g.K, P = a.g.P, M = a.g.M, q = a.q, nb = K * M + K, ldb = a.hbmax + 1;
   size_t n = q * q + 3 * P * q + nb * P * (3 + ldb);
-  if (a.hbmax > 0) n += P * P + 2 * nb * P * DB_PMAX;
+  if (a.hbmax > 0) n += P * P + nb * P * DB_PITCH;
   return sizeof(double) * (n + 2);
 }
 int launch_draw_blocks(const DrawArgs& a, cudaStream_t s) {

@@ -219,6 +219,8 @@ struct bfmmm_sampler {
     vecd sigma, alpha3;
   } rec;
   vecd work, Prec, C, Lc, rhs, v1, v2, zdraw;
+  vecd fc_C, fc_Mt;          // block draws of one update: current coefficients (q x P) and M_b = sum_a S_ab c_a
+  bool fc_valid = false;
   // ---- device-resident sweep (globals_kernels.cu): the chain's globals live in device memory, the sweep is a queue
   // of kernels, the host vectors above are a mirror refreshed on demand (dev_pull)
   struct Dev {
@@ -384,15 +386,29 @@ int block_draw_band(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, 
   const double sc = beta / s->sigma_sq;
   const int hg = s->identity ? 0 : s->hbG, hb = std::max(hg, prior_full ? s->hbP : 0), ldb = hb + 1;
   s->v1.assign(P, 0.0); s->v2.resize(P); s->rhs.resize(P);
-  for (int kk = 0; kk < s->K; kk++)
-    for (int m2 = 0; m2 <= s->M; m2++)
-      for (int d2 = 0; d2 <= s->D; d2++) {
-        const int b = s->feat(kk, m2, d2);
-        if (b == a) continue;
-        const double sab = WtW[(size_t)b * q + a];
-        get_coef(s, kk, m2, d2, s->v2.data());
-        for (int p = 0; p < P; p++) s->v1[p] += sab * s->v2[p];
+  // coefficients C (q x P) and M_b = sum_a' S_a'b c_a' (q x P) of the current update: built at its first block, then
+  // kept current with a rank-one update per drawn block (the statements of draw_blocks_kernel)
+  if (!s->fc_valid) {
+    s->fc_C.assign((size_t)q * P, 0.0); s->fc_Mt.assign((size_t)q * P, 0.0);
+    for (int kk = 0; kk < s->K; kk++)
+      for (int m2 = 0; m2 <= s->M; m2++)
+        for (int d2 = 0; d2 <= s->D; d2++) get_coef(s, kk, m2, d2, &s->fc_C[(size_t)s->feat(kk, m2, d2) * P]);
+    for (int b = 0; b < q; b++)
+      for (int f = 0; f < q; f++) {
+        const double sfb = WtW[(size_t)f * q + b];
+        if (sfb == 0.0) continue;
+        const double* cf = &s->fc_C[(size_t)f * P];
+        double* mb = &s->fc_Mt[(size_t)b * P];
+        for (int p = 0; p < P; p++) mb[p] += sfb * cf[p];
       }
+    s->fc_valid = true;
+  }
+  {
+    const double saa0 = WtW[(size_t)a * q + a];
+    const double* ca = &s->fc_C[(size_t)a * P];
+    const double* ma = &s->fc_Mt[(size_t)a * P];
+    for (int p = 0; p < P; p++) s->v1[p] = ma[p] - saa0 * ca[p];          // sum_{b != a} S_ab c_b
+  }
   for (int r = 0; r < P; r++) {
     double gv = 0;
     if (s->identity) gv = s->v1[r];
@@ -417,6 +433,16 @@ int block_draw_band(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, 
   if (!band_chol_upper_rev_rd(P, hb, ldb, A, A, rd)) return -1;
   band_draw_rd(P, hb, ldb, A, rd, s->rhs.data(), z, x, w);
   set_coef(s, k, mm, dd, x);
+  {
+    double* ca = &s->fc_C[(size_t)a * P];
+    for (int p = 0; p < P; p++) { w[p] = x[p] - ca[p]; ca[p] = x[p]; }
+    for (int b = 0; b < q; b++) {
+      const double sab = WtW[(size_t)a * q + b];
+      if (sab == 0.0) continue;
+      double* mb = &s->fc_Mt[(size_t)b * P];
+      for (int p = 0; p < P; p++) mb[p] += sab * w[p];
+    }
+  }
   return 0;
 }
 
@@ -529,6 +555,7 @@ int block_draw(bfmmm_sampler* s, int k, int mm, int dd, const double* WtW, const
     }
   }
   set_coef(s, k, mm, dd, s->v1.data());
+  s->fc_valid = false;            // the band path's running sums no longer match the coefficients
   return 0;
 }
 
@@ -1122,6 +1149,7 @@ int bfmmm_host_update_A_xi(bfmmm_sampler* s) {
 // updatePhi (UpdatePhi.h:23-89): blocks (j, m), prior diag(tilde_tau(j,m) * gamma(j,.,m))
 int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   if (dev_begin_host_update(s)) return 1;
+  s->fc_valid = false;
   const int K = s->K, P = s->P, M = s->M;
   s->blk_purpose = HP_PHI; s->blk_index = 0;
   vecd diag(P);
@@ -1154,6 +1182,7 @@ int bfmmm_host_update_phi(bfmmm_sampler* s, const double* WtW, const double* BtY
 // updateNu (UpdateNu.h:24-74): blocks j, prior tau_j * P (MV: (1/tau_j) I, :195-196)
 int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   if (dev_begin_host_update(s)) return 1;
+  s->fc_valid = false;
   const int K = s->K, P = s->P;
   s->blk_purpose = HP_NU; s->blk_index = 0;
   vecd diag(P);
@@ -1195,6 +1224,7 @@ int bfmmm_host_update_nu(bfmmm_sampler* s, const double* WtW, const double* BtYW
 // updateEta (UpdateEta.h:28-94): d outer, j inner; prior tau_eta(j,d) * P (MV: (1/tau_eta) I)
 int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   if (dev_begin_host_update(s)) return 1;
+  s->fc_valid = false;
   const int K = s->K, P = s->P, D = s->D;
   s->blk_purpose = HP_ETA; s->blk_index = 0;
   vecd& prior = s->prior_buf;
@@ -1215,6 +1245,7 @@ int bfmmm_host_update_eta(bfmmm_sampler* s, const double* WtW, const double* BtY
 // updateXiCovariateAdj (UpdateXi.h:26-93): order j, m, d; prior diag(tilde_tau_xi(j,m,d) * gamma_xi_j(.,d,m))
 int bfmmm_host_update_xi(bfmmm_sampler* s, const double* WtW, const double* BtYW, double beta) {
   if (dev_begin_host_update(s)) return 1;
+  s->fc_valid = false;
   const int K = s->K, P = s->P, M = s->M, D = s->D;
   s->blk_purpose = HP_XI; s->blk_index = 0;
   vecd diag(P);

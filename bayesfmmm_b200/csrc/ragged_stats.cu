@@ -25,6 +25,11 @@ __device__ __forceinline__ void dmma884r(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void rs_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 // Work layout: the output (band rows x feature pairs) is cut into S = gy * gz slices of RS_MTB m-tiles x NTB
 // pair-tiles (what one warp can accumulate in registers); the EIGHT WARPS of a block take eight different
 // slices of the SAME 8-function chunk, so the feature weights of a chunk are formed once per block
@@ -34,7 +39,8 @@ __device__ __forceinline__ void dmma884r(double& d0, double& d1, double a, doubl
 template <int NTB>
 __global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const RaggedStatsArgs a, int gy, int gz) {
   constexpr int TILES = RS_MTB * NTB;
-  __shared__ double s_w[2][RS_QMAX][8];
+  __shared__ double2 s_av[2][RS_MTB][RS_THREADS];
+  __shared__ double s_w[2][RS_QMAX + 1][8];    // row q stays zero: the weight row of "no pair"
   __shared__ double s_base[2][RS_BASEMAX][8];
   __shared__ uchar4 s_feat[RS_QMAX];          // feature -> rows of s_base: (Z row, chi row or 255, X row or 255)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -49,17 +55,19 @@ __global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const Ragge
     s_feat[f] = make_uchar4((unsigned char)k, mm > 0 ? (unsigned char)(a.K + mm - 1) : 255,
                             dd > 0 ? (unsigned char)(a.K + a.M + dd - 1) : 255, 0);
   }
+  if (threadIdx.x < 16) s_w[threadIdx.x >> 3][a.q][threadIdx.x & 7] = 0.0;
   const int nbase = a.K + a.M + a.D;
-  // pair (fa <= fb) of this lane in each pair-tile: index -> row-major upper triangle
+  // pair (fa <= fb) of this lane in each pair-tile: index -> row-major upper triangle; kept as the byte offsets of
+  // the two weight rows in s_w (-1: no pair), so the hot loop forms an address with one add
   int pa[NTB], pb[NTB];
 #pragma unroll
   for (int nt = 0; nt < NTB; nt++) {
     int pf = (zs * NTB + nt) * 8 + g, fa = 0;
-    pa[nt] = 255; pb[nt] = 255;
+    pa[nt] = (a.q * 8 + 2 * c) * 8; pb[nt] = pa[nt];       // the zero row: no branch in the hot loop
     if (active && pf < a.npairs) {
       int rem = pf;
       while (rem >= a.q - fa) { rem -= a.q - fa; fa++; }
-      pa[nt] = fa; pb[nt] = fa + rem;
+      pa[nt] = (fa * 8 + 2 * c) * 8; pb[nt] = ((fa + rem) * 8 + 2 * c) * 8;
     }
   }
   const double* ap[RS_MTB];
@@ -82,17 +90,29 @@ __global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const Ragge
   const int n_chunks = a.ld >> 3;
   int ch = blockIdx.x;
   double nextv = (ssrc && ch < n_chunks) ? ssrc[(ch << 3) + slot] : 0.0;
+  // The band rows (A operand) travel global -> shared with cp.async (LDGSTS, 16 bytes per thread, L1 bypassed) into
+  // thread-private slots, one chunk AHEAD: the ~600 cycles of global-load latency hide behind the ~650 cycles of
+  // tensor-pipe work of the current chunk instead of stalling every chunk, and nothing waits in registers.
+  auto issue = [&](int stage, int chunk) {
+    if (chunk < n_chunks) {
+#pragma unroll
+      for (int mt = 0; mt < RS_MTB; mt++)
+        if (ap[mt]) rs_cp_async16(&s_av[stage][mt][threadIdx.x], ap[mt] + (chunk << 3) + 2 * c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0, ch);
   __syncthreads();
   for (int it = 0; ch < n_chunks; ch += gridDim.x, it++) {
     const int buf = it & 1;
-    const int i8 = ch << 3;
     if (ssrc) s_base[buf][srow][slot] = nextv;
+    const int chn = ch + gridDim.x;
+    issue(buf ^ 1, chn);
+    if (ssrc && chn < n_chunks) nextv = ssrc[(chn << 3) + slot];        // in flight while this chunk is consumed
+    asm volatile("cp.async.wait_group 1;" ::: "memory");                // the group of the current chunk has landed
     double2 av[RS_MTB];
 #pragma unroll
-    for (int mt = 0; mt < RS_MTB; mt++)
-      av[mt] = ap[mt] ? __ldcs(reinterpret_cast<const double2*>(ap[mt] + i8 + 2 * c)) : make_double2(0.0, 0.0);
-    const int chn = ch + gridDim.x;
-    if (ssrc && chn < n_chunks) nextv = ssrc[(chn << 3) + slot];        // in flight while this chunk is consumed
+    for (int mt = 0; mt < RS_MTB; mt++) av[mt] = ap[mt] ? s_av[buf][mt][threadIdx.x] : make_double2(0.0, 0.0);
     __syncthreads();
     for (int f = srow; f < a.q; f += RS_THREADS / 8) {                  // feature weights, once per block
       const uchar4 t = s_feat[f];
@@ -105,12 +125,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2) ragged_stats_kernel(const Ragge
     if (active) {
 #pragma unroll
       for (int nt = 0; nt < NTB; nt++) {
-        double2 wv = make_double2(0.0, 0.0);
-        if (pa[nt] != 255) {
-          const double2 wa = *reinterpret_cast<const double2*>(&s_w[buf][pa[nt]][2 * c]);
-          const double2 wb = *reinterpret_cast<const double2*>(&s_w[buf][pb[nt]][2 * c]);
-          wv.x = wa.x * wb.x; wv.y = wa.y * wb.y;
-        }
+        const char* wbase = reinterpret_cast<const char*>(&s_w[buf][0][0]);
+        const double2 wa = *reinterpret_cast<const double2*>(wbase + pa[nt]);
+        const double2 wb = *reinterpret_cast<const double2*>(wbase + pb[nt]);
+        const double2 wv = make_double2(wa.x * wb.x, wa.y * wb.y);
 #pragma unroll
         for (int mt = 0; mt < RS_MTB; mt++) {
           dmma884r(R[mt][nt][0], R[mt][nt][1], av[mt].x, wv.x);
