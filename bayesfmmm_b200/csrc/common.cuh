@@ -283,6 +283,8 @@ int launch_z_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_chi_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_moments(const PassArgs& a, int K, int M, double* mom, cudaStream_t s);          // moments_kernels.cu
+int launch_chi_draw(const PassArgs& a, int K, int M, const double* mom, cudaStream_t s);
 int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_mloglik(const PassArgs& a, int K, int M, bool ragged, cudaStream_t s);

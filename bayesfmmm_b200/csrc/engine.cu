@@ -48,6 +48,10 @@ struct bfmmm_engine {
   int bw = 0, npairs = 0;
   bool ragged = false;
   double *snapZ = nullptr, *snapChi = nullptr;   // device copy of (Z, chi) for tempered transitions
+  // per-function moments (r[0..M-1], rss + |c~ - mu~|^2) left by the SSR pass for the chi step that follows it
+  // (moments_kernels.cu); valid until Z, the globals or the data change
+  double* mom = nullptr;
+  bool mom_valid = false, mom_enabled = false;
   double *ni = nullptr;                          // ragged grids: points per function (marginal log-likelihood)
   double *cpo_m = nullptr, *cpo_s = nullptr, *logl = nullptr;   // CPO accumulators, per-function marginal log-likelihood
   int64_t cpo_count = 0;
@@ -107,7 +111,7 @@ void free_all(bfmmm_engine* e) {
   cudaSetDevice(e->device);
   cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
   cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
-  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi);
+  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi); cudaFree(e->mom);
   cudaFree(e->Hh); cudaFree(e->Gl); cudaFree(e->rs_partials);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->ev_snap) cudaEventDestroy(e->ev_snap);
@@ -442,6 +446,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     e->sum_half = (double)e->n * (double)(e->T / 2);             // sum_i floor(n_i / 2), UpdateSigma.h:49
   }
   if (e->D && upload_cols(e, e->X, c->X, e->D)) return bail(1);
+  e->mom_enabled = !e->ragged && e->D == 0 && e->M >= 1 && e->M <= 6 && e->K >= 2 && e->K <= 6 && !std::getenv("BFMMM_NO_MOMENTS");
   e->tma.valid = 0;
   if (!e->ragged) bf::stats_tma_setup(&e->tma, e->Ct, e->Z, e->chi, e->X, e->ld, e->Pc, e->K, e->M, e->D, e->q);
   CUE(cudaStreamSynchronize(e->stream));
@@ -479,6 +484,7 @@ int bfmmm_get_gram(bfmmm_engine* e, double* G) {
 int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
+  if (Z) e->mom_valid = false;
   if (Z && upload_cols(e, e->Z, Z, e->K)) return 1;
   if (chi && upload_cols(e, e->chi, chi, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
@@ -544,6 +550,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
   if (!(sigma_sq > 0)) return fail("bfmmm_set_globals: sigma_sq must be positive");
   CU(cudaSetDevice(e->device));
   const int K = e->K, P = e->P, M = e->M, D = e->D, QS = e->QS;
+  e->mom_valid = false;
   int slot = e->stage_next;
   e->stage_next = (slot + 1) % N_STAGE;
   CU(cudaEventSynchronize(e->ev_stage[slot]));
@@ -604,6 +611,7 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
                     bool dump_draws, const double* zpar_dev = nullptr) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
+  e->mom_valid = false;
   a.zpar_dev = zpar_dev;
   a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM); a.inv_a_Z_PM = 1.0 / a_Z_PM;
   double digam_a = 0;
@@ -646,7 +654,7 @@ int bfmmm_update_z(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_
   return 0;
 }
 
-static int chi_launch(bfmmm_engine* e, double beta, bool injected, const double* sigma_dev = nullptr) {
+static int chi_launch(bfmmm_engine* e, double beta, bool injected, const double* sigma_dev = nullptr, bool dump_draws = false) {
   bf::PassArgs a;
   fill_pass(e, a, beta);
   if (e->sigma_armed) { a.sigma_dev = e->sigma_dev; e->sigma_armed = false; }
@@ -657,8 +665,12 @@ static int chi_launch(bfmmm_engine* e, double beta, bool injected, const double*
     a.grid_reserve = 1;
   }
   if (injected) a.eps = e->draws;
+  if (dump_draws) a.draws_out = e->draws;
   a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
-  int rc = e->ragged ? bf::launch_chi_ragged(a, e->K, e->M, e->stream) : bf::launch_chi(a, e->K, e->M, e->stream);
+  // the SSR pass that preceded this step left the moments of the same (Z, globals): draw from them, no second data pass
+  int rc = e->mom_valid ? bf::launch_chi_draw(a, e->K, e->M, e->mom, e->stream)
+           : e->ragged  ? bf::launch_chi_ragged(a, e->K, e->M, e->stream)
+                        : bf::launch_chi(a, e->K, e->M, e->stream);
   if (rc) return fail("chi kernel launch failed rc=" + std::to_string(rc));
   return 0;
 }
@@ -684,7 +696,14 @@ int bfmmm_ssr_async(bfmmm_engine* e) {
   bf::PassArgs a;
   fill_pass(e, a, 1.0);
   a.out = e->stats + e->off_ssr(); a.n_out = 1;
-  int rc = e->ragged ? bf::launch_ssr_ragged(a, e->K, e->M, e->stream) : bf::launch_ssr(a, e->K, e->M, e->stream);
+  int rc;
+  if (e->mom_enabled) {          // common basis, no covariates: the pass also leaves the chi step's moments
+    if (!e->mom) CU(cudaMalloc(&e->mom, (size_t)e->ld * (e->M + 1) * 8));
+    rc = bf::launch_moments(a, e->K, e->M, e->mom, e->stream);
+    e->mom_valid = (rc == 0);
+  } else {
+    rc = e->ragged ? bf::launch_ssr_ragged(a, e->K, e->M, e->stream) : bf::launch_ssr(a, e->K, e->M, e->stream);
+  }
   if (rc) return fail("ssr kernel launch failed rc=" + std::to_string(rc));
   return 0;
 }
@@ -840,6 +859,7 @@ int bfmmm_state_snapshot(bfmmm_engine* e) {
 int bfmmm_state_restore(bfmmm_engine* e) {
   if (!e || !e->snapZ) return fail("bfmmm_state_restore: no snapshot");
   CU(cudaSetDevice(e->device));
+  e->mom_valid = false;
   CU(cudaMemcpyAsync(e->Z, e->snapZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
   CU(cudaMemcpyAsync(e->chi, e->snapChi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
@@ -932,16 +952,13 @@ int bfmmm_debug_update_z_rng(bfmmm_engine* e, const double* pi, double alpha3, d
 int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
-  bf::PassArgs a;
-  fill_pass(e, a, beta);
-  a.draws_out = e->draws;
-  a.out = e->stats + e->off_ssr_after(); a.n_out = 1;
-  if (e->ragged ? bf::launch_chi_ragged(a, e->K, e->M, e->stream) : bf::launch_chi(a, e->K, e->M, e->stream))
-    return fail("chi kernel launch failed");
+  if (chi_launch(e, beta, false, nullptr, true)) return 1;
   if (download_cols(e, eps_out, e->draws, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
   return 0;
 }
+// 1 when the next bfmmm_update_chi will draw from the moments the last SSR pass left (moments_kernels.cu)
+int bfmmm_debug_moments_valid(bfmmm_engine* e) { return e && e->mom_valid ? 1 : 0; }
 // the projected cache itself: C~ (n x P column-major) and rss (n)
 int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
   if (!e) return fail("null engine");
@@ -961,6 +978,7 @@ int bfmmm_engine_devinfo(bfmmm_engine* e, bf::EngineDevInfo* o) {
   o->L_host = e->L.data(); o->stream = e->stream; o->device = e->device; o->stats_len = e->stats_len;
   return 0;
 }
+void bfmmm_moments_invalidate(bfmmm_engine* e) { if (e) e->mom_valid = false; }
 // Z step with pi, alpha_3 and sigma^2 read from device memory ([pi (8) | alpha_3 | sigma^2])
 int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const double* zpar_dev) {
   if (!e || !zpar_dev) return fail("null argument");

@@ -21,3 +21,4 @@ int bfmmm_engine_devinfo(bfmmm_engine* e, bf::EngineDevInfo* out);
 int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const double* zpar_dev);
 int bfmmm_update_chi_async_p(bfmmm_engine* e, double beta, const double* sigma_dev);
 int bfmmm_set_sigma(bfmmm_engine* e, double sigma_sq);
+void bfmmm_moments_invalidate(bfmmm_engine* e);   // the caller changed the staged globals behind the engine's back

@@ -802,6 +802,7 @@ int sampler_step_device(bfmmm_sampler* s, int sweep, double beta) {
   da.do_phi = do_phi ? 1 : 0; da.do_nu = do_nu ? 1 : 0; da.rng = rng; da.err = d.err;
   da.clk = d.clk;
   if (launch_draw_blocks(da, st)) return sfail("draw_blocks kernel launch failed");
+  bfmmm_moments_invalidate(e);          // the kernel writes the staged globals
   CUS(cudaEventRecord(d.ev_drawn, st));
   if (bfmmm_ssr_async(e)) return 1;                                                 // updateSigma's data pass, new globals
   if (s->allreduce && s->allreduce(s->allreduce_ctx, d.info.stats + s->K + 1, 1, st)) return sfail("all-reduce hook failed");

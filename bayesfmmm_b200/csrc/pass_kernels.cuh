@@ -572,6 +572,53 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
 //   (y - B mu)' cov^{-1} (y - B mu) = (|y - B mu|^2 - r'(sigma^2 I_M + G)^{-1} r) / sigma^2
 // (matrix determinant lemma / Woodbury), so the n_i x n_i covariance the reference factorises never exists.
 // The CPO's harmonic mean over iterations is kept as a running log-sum-exp of -logl per function.
+// Common basis without covariates: u_m = sum_k z_k phi~_km, so the per-function Gram is a quadratic form in z,
+//   G_i[m][n] = u_m . u_n = sum_{k <= k'} z_k z_k' Q[mn][kk'],   Q[mn][kk'] = phi~_km . phi~_k'n (+ phi~_k'm . phi~_kn, k != k'),
+// with Q a property of the globals only: every block builds it once from the staged globals.
+template <int K, int M>
+__device__ __forceinline__ void build_gram_forms(const PassArgs& a, const double* g, double* Qs) {
+  constexpr int NKK = K * (K + 1) / 2, NMN = M * (M + 1) / 2;
+  for (int idx = threadIdx.x; idx < NMN * NKK; idx += blockDim.x) {
+    int mn = idx / NKK, kk = idx % NKK, m = 0, n = 0, k = 0, k2 = 0;
+    for (int t = mn; t >= M - m; t -= M - m, m++) {}
+    { int t = mn; for (int j = 0; j < m; j++) t -= M - j; n = m + t; }
+    for (int t = kk; t >= K - k; t -= K - k, k++) {}
+    { int t = kk; for (int j = 0; j < k; j++) t -= K - j; k2 = k + t; }
+    const int f1 = k * (M + 1) + m + 1, f2 = k2 * (M + 1) + n + 1, f3 = k2 * (M + 1) + m + 1, f4 = k * (M + 1) + n + 1;
+    double q1 = 0, q2 = 0;
+    for (int p = 0; p < a.P4; p++) {
+      const double* gp = g + p * a.QS;
+      q1 = fma(gp[f1], gp[f2], q1);
+      q2 = fma(gp[f3], gp[f4], q2);
+    }
+    Qs[idx] = (k == k2) ? q1 : q1 + q2;
+  }
+  __syncthreads();
+}
+// upper triangle of G_i from the forms and z
+template <int K, int M>
+__device__ __forceinline__ void gram_from_forms(const double* Qs, const double (&z)[K], double (&G)[M][M]) {
+  constexpr int NKK = K * (K + 1) / 2;
+  double zz[NKK];
+  {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+      for (int k2 = k; k2 < K; k2++, t++) zz[t] = z[k] * z[k2];
+  }
+  int mn = 0;
+#pragma unroll
+  for (int m = 0; m < M; m++)
+#pragma unroll
+    for (int q = m; q < M; q++, mn++) {
+      double t = 0;
+#pragma unroll
+      for (int kk = 0; kk < NKK; kk++) t = fma(Qs[mn * NKK + kk], zz[kk], t);
+      G[m][q] = t;
+    }
+}
+
 template <int K, int M, bool COV, int V, bool RG, bool CPO = false>
 #ifndef BF_CHI_MINB
 #define BF_CHI_MINB 4      // resident blocks per SM targeted by the V = 2 chi kernel (3: 68 us, 4: 66 us, 5: 83 us, 6: 134 us -- spills)
@@ -591,24 +638,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
   constexpr bool GQ = !COV && !RG;
   constexpr int NKK = K * (K + 1) / 2, NMN = M * (M + 1) / 2;
   __shared__ __align__(16) double Qs[GQ ? NMN * NKK : 1];
-  if constexpr (GQ) {
-    for (int idx = threadIdx.x; idx < NMN * NKK; idx += blockDim.x) {
-      int mn = idx / NKK, kk = idx % NKK, m = 0, n = 0, k = 0, k2 = 0;
-      for (int t = mn; t >= M - m; t -= M - m, m++) {}
-      { int t = mn; for (int j = 0; j < m; j++) t -= M - j; n = m + t; }
-      for (int t = kk; t >= K - k; t -= K - k, k++) {}
-      { int t = kk; for (int j = 0; j < k; j++) t -= K - j; k2 = k + t; }
-      const int f1 = k * (M + 1) + m + 1, f2 = k2 * (M + 1) + n + 1, f3 = k2 * (M + 1) + m + 1, f4 = k * (M + 1) + n + 1;
-      double q1 = 0, q2 = 0;
-      for (int p = 0; p < a.P4; p++) {
-        const double* gp = g + p * a.QS;
-        q1 = fma(gp[f1], gp[f2], q1);
-        q2 = fma(gp[f3], gp[f4], q2);
-      }
-      Qs[idx] = (k == k2) ? q1 : q1 + q2;
-    }
-    __syncthreads();
-  }
+  if constexpr (GQ) build_gram_forms<K, M>(a, g, Qs);
   double red[1] = {0};
   const double bs = a.beta / (a.sigma_dev ? *a.sigma_dev : a.sigma_sq);
   for (int i0 = (blockIdx.x * PF_THREADS + threadIdx.x) * V; i0 < a.ld; i0 += gridDim.x * PF_THREADS * V) {
@@ -671,27 +701,11 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_CHI1_MINB : (
       });
 #pragma unroll
       for (int v = 0; v < V; v++) {
-        double zz[NKK];
-        {
-          int t = 0;
 #pragma unroll
-          for (int k = 0; k < K; k++)
-#pragma unroll
-            for (int k2 = k; k2 < K; k2++, t++) zz[t] = st.z[v][k] * st.z[v][k2];
-        }
-        int mn = 0;
-#pragma unroll
-        for (int m = 0; m < M; m++) {
+        for (int m = 0; m < M; m++)
 #pragma unroll
           for (int k = 0; k < K; k++) r[v][m] = fma(st.z[v][k], sk[v][k][m], r[v][m]);
-#pragma unroll
-          for (int q = m; q < M; q++, mn++) {
-            double t = 0;
-#pragma unroll
-            for (int kk = 0; kk < NKK; kk++) t = fma(Qs[mn * NKK + kk], zz[kk], t);
-            G[v][m][q] = t;
-          }
-        }
+        gram_from_forms<K, M>(Qs, st.z[v], G[v]);
       }
     } else {
     Coef<K, M, COV, V> cf;
@@ -921,8 +935,8 @@ __global__ void __launch_bounds__(PF_THREADS) ssr_kernel(const PassArgs a) {
   X(6, 1) X(6, 2) X(6, 3) X(6, 4) X(6, 5) X(6, 6)
 #endif
 
-template <int V, typename Kern>
-inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extra_smem = 0) {
+template <int V, typename Kern, typename... Extra>
+inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extra_smem = 0, Extra... extra) {
   size_t smem = (size_t)a.P4 * a.QS * sizeof(double) + extra_smem;
   // resident blocks per SM of this instantiation (queried once), grid = one full wave
   // (kernel, device) -> (smem, blocks per SM): the attribute and the occupancy are per device; several host threads
@@ -953,7 +967,7 @@ inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extr
   if (grid < 1) grid = 1;
   if (grid > need) grid = need;
   if (grid > a.max_blocks) grid = a.max_blocks;
-  kern<<<grid, PF_THREADS, smem, s>>>(a);
+  kern<<<grid, PF_THREADS, smem, s>>>(a, extra...);
   g_launch_count++;
   return (int)cudaGetLastError();
 }

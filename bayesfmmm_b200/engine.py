@@ -272,6 +272,10 @@ class Engine:
         self._chk(self._lib.bfmmm_debug_update_chi_rng(self._h, C.c_double(beta), _p(eps)))
         return eps
 
+    def debug_moments_valid(self):
+        """True when the next update_chi draws from the moments the preceding ssr() left."""
+        return bool(self._lib.bfmmm_debug_moments_valid(self._h))
+
     def debug_get_cache(self):
         Ct = np.zeros((self.n, self.P), order="F")
         rss = np.zeros(self.n)

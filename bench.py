@@ -550,10 +550,21 @@ def run_ours(a):
     g = smp.get()
     pi_now, a3 = g["pi"], g["alpha3"]
     ab = algorithmic_bytes(a, n, eng)
-    kern = {"z_kernel": kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM)),
-            "chi_kernel": kernel_ms(lambda: eng.update_chi_async()),
-            "ssr_kernel": kernel_ms(lambda: eng.ssr_async()),
-            "stats_kernels": kernel_ms(lambda: eng.suffstats_async())}
+    kern = {"z_kernel": kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM))}
+    t_ssr = kernel_ms(lambda: eng.ssr_async())
+    if eng.debug_moments_valid():
+        # common basis, no covariates: updateSigma's pass leaves the per-function moments and updateChi draws from them
+        # (csrc/moments_kernels.cu) -- the sweep's two kernels are these, not ssr_kernel + chi_kernel
+        n8 = n * 8
+        kern["moments_kernel"] = t_ssr
+        kern["chi_draw_kernel"] = kernel_ms(lambda: eng.update_chi_async())
+        ab["moments_kernel"] = n8 * (w["P"] + 1 + K + M + (M + 1))
+        ab["chi_draw_kernel"] = n8 * (K + M + (M + 1) + M)
+        del ab["ssr_kernel"], ab["chi_kernel"]
+    else:
+        kern["ssr_kernel"] = t_ssr
+        kern["chi_kernel"] = kernel_ms(lambda: eng.update_chi_async())
+    kern["stats_kernels"] = kernel_ms(lambda: eng.suffstats_async())
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -13,6 +13,9 @@ int bfmmm_debug_get_acc(bfmmm_engine* e, double* acc /* n */);
 int bfmmm_debug_update_z_rng(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta,
                              double* gam_out /* n x K */, double* u_out /* n */);
 int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out /* n x M */);
+/* 1 when the next bfmmm_update_chi will draw from the per-function moments the preceding bfmmm_ssr left (common basis,
+ * no covariates), 0 when it will make its own pass over the cache */
+int bfmmm_debug_moments_valid(bfmmm_engine* e);
 /* the projected cache: whitened coefficients (n x P column-major) and orthogonal residual norms */
 int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss);
 /* the device routines of csrc/fastmath.cuh applied elementwise (host buffers): which = 0 log, 1 reciprocal,

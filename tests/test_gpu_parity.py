@@ -57,10 +57,17 @@ def test_update_z(name, beta):
 
 @pytest.mark.parametrize("name", GPU_CASES)
 @pytest.mark.parametrize("beta", [1.0, 0.6])
-def test_update_chi_and_ssr_after(name, beta):
+@pytest.mark.parametrize("after_ssr", [False, True])
+def test_update_chi_and_ssr_after(name, beta, after_ssr):
+    """updateChi on its own (chi_kernel's pass over the cache) and right after the SSR pass of updateSigma, the order of
+    the sweep: on a common basis without covariates the SSR pass leaves the per-function moments and the chi step draws
+    from them without a second pass (moments_kernels.cu).  Both must give the oracle's chi."""
     s, d, st, eng = engine_for(name)
     dr = cases.draws(name, s)
     chi_o = orc.update_chi(d, st, dr["eps"], beta)
+    if after_ssr:
+        assert rel(eng.ssr()[0], orc.ssr(d, st)[0]) < TOL
+        assert eng.debug_moments_valid() == (cases.CASES[name][0] in ("common", "mv", "hd") and d.D == 0 and d.M >= 1)
     ssr_after = eng.update_chi(beta, eps=dr["eps"])
     _, chi_g = eng.get_state(Z=False)
     assert rel(chi_g, chi_o) < TOL
@@ -177,6 +184,12 @@ def test_device_rng_replay(name):
     _, chi_g = eng.get_state(Z=False)
     assert rel(chi_g, orc.update_chi(d, st, eps)) < TOL
     assert abs(eps.mean()) < 5 / np.sqrt(eps.size)
+    # the same step drawn from the moments the SSR pass leaves (the sweep's order): same normals, same chi
+    eng.set_state(s["Z"], s["chi"])
+    eng.ssr()
+    eps_m = eng.debug_update_chi_rng()
+    _, chi_m = eng.get_state(Z=False)
+    assert np.array_equal(eps_m, eps) and rel(chi_m, chi_g) < TOL
     # determinism and shard-independence: same seed -> same draws; a shard starting at global
     # offset 8 reproduces rows 8.. of the full run
     eng.set_state(s["Z"], s["chi"])
