@@ -44,7 +44,7 @@ EXPORTS = [
     # include/bfmmm_post.h
     "bfmmm_quantiles",
     "bfmmm_debug_enable_acc", "bfmmm_debug_get_acc", "bfmmm_debug_update_z_rng", "bfmmm_debug_update_chi_rng",
-    "bfmmm_debug_get_cache", "bfmmm_debug_fastmath", "bfmmm_debug_moments_valid",
+    "bfmmm_debug_get_cache", "bfmmm_debug_fastmath", "bfmmm_debug_moments_valid", "bfmmm_debug_z_propose",
 ]
 
 

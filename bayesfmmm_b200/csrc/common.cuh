@@ -46,6 +46,8 @@ struct PassArgs {
   const double* __restrict__ gam;   // injected draws [K][ld] or nullptr (device RNG)
   const double* __restrict__ u;     // [ld] or nullptr
   const double* __restrict__ eps;   // chi: [M][ld] or nullptr
+  const double* __restrict__ zprop; // Z step, accept half: (z*[K] | lr | lu)[ld] made by z_propose_kernel
+  double* __restrict__ zprop_out;   // Z step, proposal half: where to leave them
   double* __restrict__ acc_out;     // optional per-function acceptance log-ratio (diagnostics)
   double* __restrict__ draws_out;   // optional: device-RNG draws written back ([K+1][ld] / [M][ld])
   // marginal log-likelihood / CPO accumulation (chi_kernel<..., CPO = true>)
@@ -283,6 +285,8 @@ int launch_z_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_chi_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
+int launch_z_propose(const PassArgs& a, int K, cudaStream_t s);                          // proposal half (any model)
+int launch_z_accept(const PassArgs& a, int K, int M, cudaStream_t s);                    // accept half, common basis
 int launch_moments(const PassArgs& a, int K, int M, double* mom, cudaStream_t s);          // moments_kernels.cu
 int launch_chi_draw(const PassArgs& a, int K, int M, const double* mom, cudaStream_t s);
 int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);

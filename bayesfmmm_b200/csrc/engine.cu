@@ -52,6 +52,18 @@ struct bfmmm_engine {
   // (moments_kernels.cu); valid until Z, the globals or the data change
   double* mom = nullptr;
   bool mom_valid = false, mom_enabled = false;
+  // Z step in two halves (z_propose_kernel / z_kernel<PRE>): the proposal of the next sweep may be made ahead of time on
+  // a side stream (bfmmm_z_propose_async); it is used when the step is asked for with exactly the parameters it was made with
+  double* zprop = nullptr;
+  bool z_split = false, prop_valid = false;
+  cudaStream_t side = nullptr;
+  int prio_side = 0;
+  double* h_slz = nullptr;        // mapped page-locked copy of [sum log Z (K) | accepts] read right behind the Z step
+  double* h_slz_dev = nullptr;
+  cudaEvent_t ev_slz = nullptr;
+  cudaEvent_t ev_zdone = nullptr, ev_prop = nullptr, ev_queued = nullptr;
+  double prop_pi[8] = {0}, prop_alpha3 = 0, prop_a = 0;
+  uint64_t prop_key = 0, prop_iter = 0;
   double *ni = nullptr;                          // ragged grids: points per function (marginal log-likelihood)
   double *cpo_m = nullptr, *cpo_s = nullptr, *logl = nullptr;   // CPO accumulators, per-function marginal log-likelihood
   int64_t cpo_count = 0;
@@ -111,7 +123,13 @@ void free_all(bfmmm_engine* e) {
   cudaSetDevice(e->device);
   cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
   cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
-  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi); cudaFree(e->mom);
+  cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi); cudaFree(e->mom); cudaFree(e->zprop);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_zdone) cudaEventDestroy(e->ev_zdone);
+  if (e->ev_prop) cudaEventDestroy(e->ev_prop);
+  if (e->ev_queued) cudaEventDestroy(e->ev_queued);
+  if (e->ev_slz) cudaEventDestroy(e->ev_slz);
+  if (e->h_slz) cudaFreeHost(e->h_slz);
   cudaFree(e->Hh); cudaFree(e->Gl); cudaFree(e->rs_partials);
   if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
   if (e->ev_snap) cudaEventDestroy(e->ev_snap);
@@ -380,7 +398,14 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     cudaError_t _e = (x);                                                       \
     if (_e != cudaSuccess) { fail(std::string(#x) + ": " + cudaGetErrorString(_e)); return bail(1); } \
   } while (0)
-  CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  {
+    // the engine's stream outranks its side stream (ahead-of-time Z proposals): when both have blocks to place, the
+    // sweep's own kernels go first
+    int least = 0, greatest = 0;
+    CUE(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    e->prio_side = least;
+    CUE(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, greatest));
+  }
   const size_t ld = e->ld;
   e->P4 = (e->P + 3) & ~3;
   CUE(cudaMalloc(&e->Ct, ld * e->P4 * 8));
@@ -446,6 +471,7 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     e->sum_half = (double)e->n * (double)(e->T / 2);             // sum_i floor(n_i / 2), UpdateSigma.h:49
   }
   if (e->D && upload_cols(e, e->X, c->X, e->D)) return bail(1);
+  e->z_split = !e->ragged && e->K >= 2 && e->K <= 6 && !std::getenv("BFMMM_Z_FUSED");
   e->mom_enabled = !e->ragged && e->D == 0 && e->M >= 1 && e->M <= 6 && e->K >= 2 && e->K <= 6 && !std::getenv("BFMMM_NO_MOMENTS");
   e->tma.valid = 0;
   if (!e->ragged) bf::stats_tma_setup(&e->tma, e->Ct, e->Z, e->chi, e->X, e->ld, e->Pc, e->K, e->M, e->D, e->q);
@@ -481,11 +507,12 @@ int bfmmm_get_gram(bfmmm_engine* e, double* G) {
   return 0;
 }
 
+static void z_written(bfmmm_engine* e);
 int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
-  if (Z) e->mom_valid = false;
   if (Z && upload_cols(e, e->Z, Z, e->K)) return 1;
+  if (Z) z_written(e);
   if (chi && upload_cols(e, e->chi, chi, e->M)) return 1;
   CU(cudaStreamSynchronize(e->stream));
   return 0;
@@ -607,17 +634,38 @@ static void polygamma01(double x, double& digam, double& trigam) {
   digam = d; trigam = t;
 }
 
-static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta, bool injected,
-                    bool dump_draws, const double* zpar_dev = nullptr) {
-  bf::PassArgs a;
-  fill_pass(e, a, beta);
-  e->mom_valid = false;
+// Z was (or is being, on the engine's stream) written by something other than the Z step
+static void z_written(bfmmm_engine* e) {
+  e->mom_valid = false; e->prop_valid = false;
+  if (e->ev_zdone) cudaEventRecord(e->ev_zdone, e->stream);
+}
+static void z_fill(bfmmm_engine* e, bf::PassArgs& a, const double* pi, double alpha3, double a_Z_PM, const double* zpar_dev) {
   a.zpar_dev = zpar_dev;
   a.alpha3 = alpha3; a.a_Z_PM = a_Z_PM; a.log_a_Z_PM = std::log(a_Z_PM); a.inv_a_Z_PM = 1.0 / a_Z_PM;
   double digam_a = 0;
   polygamma01(a_Z_PM, digam_a, a.trigam_a);
   a.c_tot = 1.0 - a.log_a_Z_PM + digam_a;
   for (int k = 0; k < e->K; k++) a.pi[k] = pi ? pi[k] : 0.0;
+}
+static int z_split_init(bfmmm_engine* e) {
+  if (e->zprop) return 0;
+  CU(cudaMalloc(&e->zprop, (size_t)e->ld * (e->K + 2) * 8));
+  CU(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, e->prio_side));
+  CU(cudaHostAlloc(&e->h_slz, 16 * 8, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer(&e->h_slz_dev, e->h_slz, 0));
+  CU(cudaEventCreateWithFlags(&e->ev_slz, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->ev_zdone, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->ev_queued, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->ev_prop, cudaEventDisableTiming));
+  return 0;
+}
+
+static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta, bool injected,
+                    bool dump_draws, const double* zpar_dev = nullptr) {
+  bf::PassArgs a;
+  fill_pass(e, a, beta);
+  e->mom_valid = false;
+  z_fill(e, a, pi, alpha3, a_Z_PM, zpar_dev);
 #ifdef BF_TUNE_V
   static const bool force_inject = std::getenv("BFMMM_Z_INJECT") != nullptr;   // tuning: time the step without the RNG
   injected = injected || force_inject;
@@ -626,7 +674,28 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
   if (dump_draws) a.draws_out = e->draws;
   a.acc_out = e->acc_dbg;
   a.out = e->stats + e->off_slz(); a.n_out = e->K + 1;
-  int rc = e->ragged ? bf::launch_z_ragged(a, e->K, e->M, e->stream) : bf::launch_z(a, e->K, e->M, e->stream);
+  int rc;
+  if (e->z_split) {
+    if (z_split_init(e)) return 1;
+    bool ahead = e->prop_valid && !injected && !dump_draws && !zpar_dev && pi && e->prop_alpha3 == alpha3 && e->prop_a == a_Z_PM &&
+                 e->prop_key == e->key && e->prop_iter == e->iteration;
+    for (int k = 0; ahead && k < e->K; k++) ahead = (e->prop_pi[k] == pi[k]);
+    e->prop_valid = false;
+    if (ahead) {
+      CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));          // made ahead of time on the side stream
+    } else {
+      CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));          // a stale proposal may still be writing the buffer
+      a.zprop_out = e->zprop;
+      rc = bf::launch_z_propose(a, e->K, e->stream);
+      if (rc) return fail("z proposal kernel launch failed rc=" + std::to_string(rc));
+    }
+    a.zprop = e->zprop; a.zprop_out = nullptr;
+    a.gam = nullptr; a.u = nullptr; a.draws_out = nullptr;
+    rc = bf::launch_z_accept(a, e->K, e->M, e->stream);
+    CU(cudaEventRecord(e->ev_zdone, e->stream));
+  } else {
+    rc = e->ragged ? bf::launch_z_ragged(a, e->K, e->M, e->stream) : bf::launch_z(a, e->K, e->M, e->stream);
+  }
   if (rc) return fail("z kernel launch failed rc=" + std::to_string(rc));
   return 0;
 }
@@ -859,8 +928,8 @@ int bfmmm_state_snapshot(bfmmm_engine* e) {
 int bfmmm_state_restore(bfmmm_engine* e) {
   if (!e || !e->snapZ) return fail("bfmmm_state_restore: no snapshot");
   CU(cudaSetDevice(e->device));
-  e->mom_valid = false;
   CU(cudaMemcpyAsync(e->Z, e->snapZ, (size_t)e->ld * e->K * 8, cudaMemcpyDeviceToDevice, e->stream));
+  z_written(e);
   CU(cudaMemcpyAsync(e->chi, e->snapChi, (size_t)e->ld * e->M * 8, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
@@ -957,6 +1026,21 @@ int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out) {
   CU(cudaStreamSynchronize(e->stream));
   return 0;
 }
+// the proposal half of the Z step alone, on the engine's stream (kernel timing; the result is not used)
+int bfmmm_debug_z_propose(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM) {
+  if (!e || !pi) return fail("null argument");
+  if (!e->z_split) return fail("bfmmm_debug_z_propose: this engine runs the Z step as one kernel");
+  CU(cudaSetDevice(e->device));
+  if (z_split_init(e)) return 1;
+  bf::PassArgs a;
+  fill_pass(e, a, 1.0);
+  z_fill(e, a, pi, alpha3, a_Z_PM, nullptr);
+  e->prop_valid = false;
+  CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));
+  a.zprop_out = e->zprop;
+  if (bf::launch_z_propose(a, e->K, e->stream)) return fail("z proposal kernel launch failed");
+  return 0;
+}
 // 1 when the next bfmmm_update_chi will draw from the moments the last SSR pass left (moments_kernels.cu)
 int bfmmm_debug_moments_valid(bfmmm_engine* e) { return e && e->mom_valid ? 1 : 0; }
 // the projected cache itself: C~ (n x P column-major) and rss (n)
@@ -978,6 +1062,54 @@ int bfmmm_engine_devinfo(bfmmm_engine* e, bf::EngineDevInfo* o) {
   o->L_host = e->L.data(); o->stream = e->stream; o->device = e->device; o->stats_len = e->stats_len;
   return 0;
 }
+// The proposal half of the NEXT Z step, on the side stream: it starts once the last writer of Z (the Z step in
+// flight) has finished and runs beside whatever the main stream does next.  (pi, alpha_3, a_Z_PM, iteration) must be the ones the step will be
+// asked for with; otherwise bfmmm_update_z* makes its own proposal and this one is dropped.
+int bfmmm_z_propose_async(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, uint64_t iteration, bool after_queued) {
+  if (!e || !pi) return fail("null argument");
+  if (!e->z_split) return 0;
+  CU(cudaSetDevice(e->device));
+  if (z_split_init(e)) return 1;
+  bf::PassArgs a;
+  fill_pass(e, a, 1.0);
+  a.iteration = iteration;
+  z_fill(e, a, pi, alpha3, a_Z_PM, nullptr);
+  a.zprop_out = e->zprop;
+  CU(cudaStreamWaitEvent(e->side, e->ev_zdone, 0));                // the last writer of Z (z_written)
+  if (after_queued) {
+    // ... and whatever the engine's stream holds right now (the statistics kernel): it shares the FP64 pipe with this
+    // kernel, so running beside it only stretches the critical path; the gap that follows it is free
+    CU(cudaEventRecord(e->ev_queued, e->stream));
+    CU(cudaStreamWaitEvent(e->side, e->ev_queued, 0));
+  }
+  int rc = bf::launch_z_propose(a, e->K, e->side);
+  if (rc) return fail("z proposal kernel launch failed rc=" + std::to_string(rc));
+  CU(cudaEventRecord(e->ev_prop, e->side));
+  for (int k = 0; k < e->K; k++) e->prop_pi[k] = pi[k];
+  e->prop_alpha3 = alpha3; e->prop_a = a_Z_PM; e->prop_key = e->key; e->prop_iter = iteration;
+  e->prop_valid = true;
+  return 0;
+}
+
+// [sum_i log Z_ik (K) | accepts] of the Z step just queued, copied to the host right behind it (the statistics kernel
+// queued next does not delay it); _wait blocks until they have arrived.  Single-shard chains only: with several shards
+// the sums must go through the exchange first.
+int bfmmm_slz_read_begin(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  if (z_split_init(e)) return 1;
+  if (bf::launch_copy_to_host(e->stats + e->off_slz(), e->h_slz_dev, e->K + 1, e->stream)) return fail("copy_to_host kernel launch failed");
+  CU(cudaEventRecord(e->ev_slz, e->stream));
+  return 0;
+}
+int bfmmm_slz_read_wait(bfmmm_engine* e, double* out) {
+  if (!e || !e->ev_slz) return fail("bfmmm_slz_read_wait: nothing to wait for");
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventSynchronize(e->ev_slz));
+  std::copy(e->h_slz, e->h_slz + e->K + 1, out);
+  return 0;
+}
+bool bfmmm_z_ahead_supported(bfmmm_engine* e) { return e && e->z_split; }
 void bfmmm_moments_invalidate(bfmmm_engine* e) { if (e) e->mom_valid = false; }
 // Z step with pi, alpha_3 and sigma^2 read from device memory ([pi (8) | alpha_3 | sigma^2])
 int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const double* zpar_dev) {

@@ -22,3 +22,7 @@ int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const do
 int bfmmm_update_chi_async_p(bfmmm_engine* e, double beta, const double* sigma_dev);
 int bfmmm_set_sigma(bfmmm_engine* e, double sigma_sq);
 void bfmmm_moments_invalidate(bfmmm_engine* e);   // the caller changed the staged globals behind the engine's back
+int bfmmm_z_propose_async(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, uint64_t iteration, bool after_queued);
+int bfmmm_slz_read_begin(bfmmm_engine* e);
+int bfmmm_slz_read_wait(bfmmm_engine* e, double* out /* K + 1 */);
+bool bfmmm_z_ahead_supported(bfmmm_engine* e);     // the Z step runs as proposal + accept kernels (common basis)

@@ -1378,8 +1378,16 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   const bool tempered = s->in_tt || beta != 1.0;
   if (bfmmm_seed(e, s->rng.key, (uint64_t)s->tick)) return 1;
   if (push_globals(s)) return 1;
+  // Z step in two kernels (common basis): the proposal of sweep t + 1 needs only Z, pi and alpha_3 of sweep t, so it is
+  // queued on a side stream as soon as pi and alpha_3 are known and runs beside the statistics kernel and the host's
+  // Gaussian block draws.  pi and alpha_3 draw from their own Philox streams, so taking them first changes nothing
+  // unless the draws come from a tape (then the reference's order is kept and nothing runs ahead).
+  static const bool z_ahead_on = !std::getenv("BFMMM_NO_Z_AHEAD");
+  const bool z_ahead = do_z && !s->rng.use_tape && z_ahead_on && bfmmm_z_ahead_supported(e);
+  const bool z_early = z_ahead && !s->allreduce;           // one shard: sum_i log Z_ik needs no exchange
   if (do_z) {                                              // updateZ_PM -> updatePi_PM -> updateAlpha3
     if (bfmmm_update_z_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, beta)) return 1;
+    if (z_early && bfmmm_slz_read_begin(e)) return 1;
   }
   // the sufficient statistics depend only on (Z, chi, X): one pass feeds Phi, nu, eta and xi
   if (bfmmm_suffstats_async(e)) return 1;
@@ -1395,6 +1403,15 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
         for (int p = 0; p < s->P; p++) { auto st = r.open(upd == 0 ? HP_PHI : HP_NU, ((uint64_t)t << 12) + (uint64_t)p); s->zpre.push_back(st.normal()); }
     }
   }
+  if (z_early) {                                           // while the statistics kernel runs
+    double slz[9];
+    { struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
+      if (bfmmm_slz_read_wait(e, slz)) return 1; }
+    if (bfmmm_host_update_pi(s, slz)) return 1;
+    if (bfmmm_host_update_alpha3(s, slz)) return 1;
+    static const bool beside = std::getenv("BFMMM_Z_AHEAD_BESIDE") != nullptr;   // experiment: run beside the statistics kernel
+    if (bfmmm_z_propose_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, (uint64_t)(s->tick + 1), !beside)) return 1;
+  }
   if (reduce_and_read(s)) return 1;
   if (s->ll_pending) {                                     // previous sweep's post-chi SSR arrived with this exchange
     s->last_ssr = st_ssr_after(s);
@@ -1409,6 +1426,11 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   // Philox stream and reads exactly what it reads in the reference's order (Phi uses the previous
   // delta/gamma, nu the previous tau; delta, A, gamma see the new Phi; tau the new nu), so the chain is
   // the one of BFMMM.h:1500-1554 -- only wall-clock placement differs.
+  if (z_ahead && !z_early) {                               // several shards: the sums have just been exchanged
+    if (bfmmm_host_update_pi(s, st_slz(s))) return 1;
+    if (bfmmm_host_update_alpha3(s, st_slz(s))) return 1;
+    if (bfmmm_z_propose_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, (uint64_t)(s->tick + 1), false)) return 1;
+  }
   s->zpre_on = !s->rng.use_tape;
   int rc_blocks = (do_phi && bfmmm_host_update_phi(s, st_wtw(s), st_btyw(s), beta)) ||   // updatePhi
                   (do_nu && bfmmm_host_update_nu(s, st_wtw(s), st_btyw(s), beta));        // updateNu
@@ -1429,7 +1451,7 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
     if (bfmmm_sigma_draw_async(e, a_sh, tempered ? beta / 2 : 0.5, s->h.beta_0, s->rng.key, s->rng.iteration, HP_SIGMA)) return 1;
     if (bfmmm_update_chi_async(e, beta)) return 1;
   }
-  if (do_z) {                                              // updatePi_PM -> updateAlpha3
+  if (do_z && !z_ahead) {                                  // updatePi_PM -> updateAlpha3
     if (bfmmm_host_update_pi(s, st_slz(s))) return 1;
     if (bfmmm_host_update_alpha3(s, st_slz(s))) return 1;
   }

@@ -17,8 +17,11 @@
 
 namespace bf {
 
+#ifndef BF_MOM_MINB
+#define BF_MOM_MINB 4
+#endif
 template <int K, int M, int V>
-__global__ void __launch_bounds__(PF_THREADS, BF_CHI_MINB) moments_kernel(const PassArgs a, double* __restrict__ mom) {
+__global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const PassArgs a, double* __restrict__ mom) {
   extern __shared__ double g[];
   stage_globals(a, g);
   constexpr int NKK = K * (K + 1) / 2, NMN = M * (M + 1) / 2;

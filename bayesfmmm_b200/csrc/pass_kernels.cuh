@@ -319,6 +319,14 @@ __device__ __forceinline__ double z_logratio_closed(const double (&sh)[K], const
   return fma(0.5 * a.trigam_a, (dts - dt) * (dts + dt), acc);
 }
 
+// Marsaglia-Tsang's acceptance test as written: log uu < x^2/2 + d (1 - v + log v), v = v1^3 (out of line: the
+// squeeze in z_candidate_round decides almost every candidate)
+static __device__ __noinline__ bool mt_accept_exact(double v1, double vv, double d, double x, double uu) {
+  const double l3 = 3.0 * fast_log_pos(v1);
+  const double R = fma(0.5 * x, x, d * (1.0 - vv + l3));
+  return (uu - 1.0 < R) || (fast_log_nl(uu) < R);
+}
+
 // One round of Marsaglia-Tsang candidates for the coordinates still pending (bit k of `pend`): three Philox blocks
 // give two Box-Muller pairs (4 normals) and four 32-bit accept uniforms.  Candidate g = d v, d = s - 1/3,
 // v = (1 + c x)^3 with s = sh (sh >= 1) or sh + 1 (boosted below); accepted when log uu < x^2/2 + d (1 - v + log v),
@@ -346,20 +354,121 @@ __device__ __forceinline__ unsigned z_candidate_round(const PassArgs& a, uint64_
     const double v1 = 1.0 + t;
     const double vv = v1 * v1 * v1;
     const bool in = t > -0.99;
-    const double l3 = 3.0 * fast_log_pos(in ? v1 : 1.0);
-    const double R = fma(0.5 * nrm[k], nrm[k], d * (1.0 - vv + l3));
     if (((pend >> k) & 1u) != 0) {
       g[k] = d * vv;
-      bool ok = in && (ua[k] - 1.0 < R);
-      if (in && !ok) ok = fast_log_nl(ua[k]) < R;      // the exact test, for the few candidates the squeeze did not decide
+      // R = x^2/2 + d (1 - v + log v) = 3 d sum_{j >= 4} (-1)^(j+1) t^j / j  >=  -(3/4) d t^4 (1 + 2|t|)  for |t| <= 1/2:
+      // a candidate with log uu <= uu - 1 below that bound is accepted without a logarithm (all but ~2e-4 of them at
+      // the default a_Z_PM); the rest take the exact test out of line
+      const double t2 = t * t;
+      bool ok = (fabs(t) <= 0.5) && (ua[k] - 1.0 < -0.75 * d * t2 * t2 * fma(2.0, fabs(t), 1.0));
+      if (in && !ok) ok = mt_accept_exact(v1, vv, d, nrm[k], ua[k]);
       if (ok) left &= ~(1u << k);
     }
   }
   return left;
 }
 
-template <int K, int M, bool COV, int V, bool RG>
-__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z_kernel(const PassArgs a) {
+// The proposal of one function and everything of the Metropolis ratio that does not need the coefficient cache:
+// z* ~ Dirichlet(a z) normalised (rdirichlet, Distributions.h:22-45), lr = log-ratio of prior and proposal densities,
+// lu = log of the Metropolis uniform.  Reads Z only -- not the globals, chi or sigma^2.
+template <int K>
+__device__ __forceinline__ void z_propose(const PassArgs& a, const double* s_par, const double (&z)[K], int idx,
+                                          double (&zp)[K], double& lr, double& lu) {
+  const uint64_t gi = a.global_offset + (uint64_t)idx;
+  const bool live = idx < a.n;
+  double sh[K], rr[K], dl[K], uacc = 0.5, sum = 0;
+  bool generic = (K > 4);        // the gamma variates must come from the generic sampler
+  bool pos = true;               // every membership is positive (and normal): the closed forms apply
+  if (a.gam) {                   // injected draws (parity)
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      sh[k] = a.a_Z_PM * z[k];
+      pos = pos && (sh[k] > 1e-290);
+      zp[k] = __ldcs(a.gam + (size_t)k * a.ld + idx); sum += zp[k];
+    }
+    uacc = __ldcs(a.u + idx);
+    generic = false;
+  } else if constexpr (K <= 4) {
+    // the first round's random words and normals do not depend on the state: the loads issued above are in
+    // flight while they are made
+    double gk[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) sh[k] = 1.0;
+    unsigned pend = (1u << K) - 1u;
+    // (sh is filled in below, after the words of round 0 are under way: z_candidate_round reads it late)
+    bool small = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      sh[k] = a.a_Z_PM * (live ? z[k] : 1.0 / K);
+      pos = pos && (sh[k] > 1e-290);                                  // false for NaN and z <= 0 too
+      small = small || (sh[k] < 1.0);
+    }
+    generic = !pos;
+    pend = z_candidate_round<K>(a, gi, 0, sh, pend, gk, uacc, true);
+    for (uint32_t round = 1; round < 24 && __any_sync(__activemask(), pend != 0); round++)
+      pend = z_candidate_round<K>(a, gi, 8 + 3 * round, sh, pend, gk, uacc, false);
+    generic = generic || (pend != 0);
+    // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are only generated by
+    // warps that contain such a function
+    if (__any_sync(__activemask(), small)) {
+      uint32_t w3[4], w4[4];
+      philox_rk(a, gi, RNG_Z_PROPOSAL, 3, w3);
+      philox_rk(a, gi, RNG_Z_PROPOSAL, 4, w4);
+      const double ub[4] = {u52(w3[0], w3[1]), u52(w3[2], w3[3]), u52(w4[0], w4[1]), u52(w4[2], w4[3])};
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        if (sh[k] < 1.0) gk[k] *= fast_exp_nonpos(fast_log_pos(ub[k]) * fast_rcp(pos ? sh[k] : 1.0));
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) { zp[k] = gk[k]; sum += gk[k]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; k++) { sh[k] = a.a_Z_PM * z[k]; pos = pos && (sh[k] > 1e-290); }
+  }
+  if (generic) {
+    double tz[K], tzp[K], tu = uacc;     // only these copies have their address taken
+#pragma unroll
+    for (int k = 0; k < K; k++) tz[k] = z[k];
+    z_slow_proposal<K>(a.key, gi, a.iteration, tz, a.a_Z_PM, tzp, &tu, live);
+    sum = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) { zp[k] = tzp[k]; sum += tzp[k]; }
+    uacc = tu;
+  }
+  if (a.draws_out) {
+#pragma unroll
+    for (int k = 0; k < K; k++) a.draws_out[(size_t)k * a.ld + idx] = zp[k];
+    a.draws_out[(size_t)K * a.ld + idx] = uacc;
+  }
+  if (a.gam || generic) {          // the reference's division (Distributions.h:39-43): same bits as the oracle
+#pragma unroll
+    for (int k = 0; k < K; k++) zp[k] = zp[k] / sum;
+  } else {                         // straight-line path: the sum of K positive normal numbers
+    const double rs = fast_rcp(sum);
+#pragma unroll
+    for (int k = 0; k < K; k++) zp[k] *= rs;
+  }
+  // ---- log-ratio of prior and proposal densities
+  bool closed = pos;
+#pragma unroll
+  for (int k = 0; k < K; k++) closed = closed && (zp[k] > 1e-290);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    rr[k] = fast_rcp(closed ? sh[k] : 1.0);
+    dl[k] = fast_log_pos(closed ? zp[k] * (a.a_Z_PM * rr[k]) : 1.0);      // log(z*_k / z_k)
+  }
+  lr = z_logratio_closed<K>(sh, rr, zp, dl, a, s_par, closed);
+  if (!closed) {
+    double tz[K], tzp[K], tpi[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { tz[k] = z[k]; tzp[k] = zp[k]; tpi[k] = s_par[k]; }
+    lr = z_logratio_exact<K>(tz, tzp, tpi, s_par[8], a.a_Z_PM);
+  }
+  lu = fast_log(uacc);
+}
+
+template <int K, int M, bool COV, int V, bool RG, bool PRE = false>
+__global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? (PRE ? 8 : BF_Z_MINB) : 4) z_kernel(const PassArgs a) {
   extern __shared__ double g[];
   // pi, alpha_3, sigma^2: kernel arguments, or device memory when the sweep's small updates run on the device
   __shared__ double s_par[10];
@@ -381,99 +490,19 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
     // the log-ratio lr of prior and proposal densities -- so that only z, z*, chi, lr and log u are live across the
     // row loop (the loop's own state is what sets the register count, not the transcendental code).
     double zp[V][K], lr[V], lu[V];
-#pragma unroll
-    for (int v = 0; v < V; v++) {
-      const uint64_t gi = a.global_offset + (uint64_t)(i0 + v);
-      const bool live = (i0 + v) < a.n;
-      double sh[K], rr[K], dl[K], uacc = 0.5, sum = 0;
-      bool generic = (K > 4);        // the gamma variates must come from the generic sampler
-      bool pos = true;               // every membership is positive (and normal): the closed forms apply
-      if (a.gam) {                   // injected draws (parity)
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          sh[k] = a.a_Z_PM * st.z[v][k];
-          pos = pos && (sh[k] > 1e-290);
-          zp[v][k] = __ldcs(a.gam + (size_t)k * a.ld + i0 + v); sum += zp[v][k];
-        }
-        uacc = __ldcs(a.u + i0 + v);
-        generic = false;
-      } else if constexpr (K <= 4) {
-        // the first round's random words and normals do not depend on the state: the loads issued above are in
-        // flight while they are made
-        double gk[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) sh[k] = 1.0;
-        unsigned pend = (1u << K) - 1u;
-        // (sh is filled in below, after the words of round 0 are under way: z_candidate_round reads it late)
-        bool small = false;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          sh[k] = a.a_Z_PM * (live ? st.z[v][k] : 1.0 / K);
-          pos = pos && (sh[k] > 1e-290);                                  // false for NaN and z <= 0 too
-          small = small || (sh[k] < 1.0);
-        }
-        generic = !pos;
-        pend = z_candidate_round<K>(a, gi, 0, sh, pend, gk, uacc, true);
-        for (uint32_t round = 1; round < 24 && __any_sync(__activemask(), pend != 0); round++)
-          pend = z_candidate_round<K>(a, gi, 8 + 3 * round, sh, pend, gk, uacc, false);
-        generic = generic || (pend != 0);
-        // shapes below 1 (tiny memberships): Gamma(s) = Gamma(s + 1) U^(1/s); the extra uniforms are only generated by
-        // warps that contain such a function
-        if (__any_sync(__activemask(), small)) {
-          uint32_t w3[4], w4[4];
-          philox_rk(a, gi, RNG_Z_PROPOSAL, 3, w3);
-          philox_rk(a, gi, RNG_Z_PROPOSAL, 4, w4);
-          const double ub[4] = {u52(w3[0], w3[1]), u52(w3[2], w3[3]), u52(w4[0], w4[1]), u52(w4[2], w4[3])};
-#pragma unroll
-          for (int k = 0; k < K; k++)
-            if (sh[k] < 1.0) gk[k] *= fast_exp_nonpos(fast_log_pos(ub[k]) * fast_rcp(pos ? sh[k] : 1.0));
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) { zp[v][k] = gk[k]; sum += gk[k]; }
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; k++) { sh[k] = a.a_Z_PM * st.z[v][k]; pos = pos && (sh[k] > 1e-290); }
-      }
-      if (generic) {
-        double tz[K], tzp[K], tu = uacc;     // only these copies have their address taken
-#pragma unroll
-        for (int k = 0; k < K; k++) tz[k] = st.z[v][k];
-        z_slow_proposal<K>(a.key, gi, a.iteration, tz, a.a_Z_PM, tzp, &tu, live);
-        sum = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++) { zp[v][k] = tzp[k]; sum += tzp[k]; }
-        uacc = tu;
-      }
-      if (a.draws_out) {
-#pragma unroll
-        for (int k = 0; k < K; k++) a.draws_out[(size_t)k * a.ld + i0 + v] = zp[v][k];
-        a.draws_out[(size_t)K * a.ld + i0 + v] = uacc;
-      }
-      if (a.gam || generic) {          // the reference's division (Distributions.h:39-43): same bits as the oracle
-#pragma unroll
-        for (int k = 0; k < K; k++) zp[v][k] = zp[v][k] / sum;
-      } else {                         // straight-line path: the sum of K positive normal numbers
-        const double rs = fast_rcp(sum);
-#pragma unroll
-        for (int k = 0; k < K; k++) zp[v][k] *= rs;
-      }
-      // ---- log-ratio of prior and proposal densities
-      bool closed = pos;
-#pragma unroll
-      for (int k = 0; k < K; k++) closed = closed && (zp[v][k] > 1e-290);
+    if constexpr (PRE) {       // made earlier by z_propose_kernel
+      double t[V];
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        rr[k] = fast_rcp(closed ? sh[k] : 1.0);
-        dl[k] = fast_log_pos(closed ? zp[v][k] * (a.a_Z_PM * rr[k]) : 1.0);      // log(z*_k / z_k)
-      }
-      lr[v] = z_logratio_closed<K>(sh, rr, zp[v], dl, a, s_par, closed);
-      if (!closed) {
-        double tz[K], tzp[K], tpi[K];
+        ldv_cs<V>(a.zprop + (size_t)k * a.ld + i0, t);
 #pragma unroll
-        for (int k = 0; k < K; k++) { tz[k] = st.z[v][k]; tzp[k] = zp[v][k]; tpi[k] = s_par[k]; }
-        lr[v] = z_logratio_exact<K>(tz, tzp, tpi, s_par[8], a.a_Z_PM);
+        for (int v = 0; v < V; v++) zp[v][k] = t[v];
       }
-      lu[v] = fast_log(uacc);
+      ldv_cs<V>(a.zprop + (size_t)K * a.ld + i0, lr);
+      ldv_cs<V>(a.zprop + (size_t)(K + 1) * a.ld + i0, lu);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; v++) z_propose<K>(a, s_par, st.z[v], i0 + v, zp[v], lr[v], lu[v]);
     }
     // ---- squared errors of the current and the proposed state
     double so[V], sn[V];
@@ -482,7 +511,7 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
     Coef<K, M, COV, V> cf;
     if constexpr (!RG) {
       const int QSc = COV ? a.QS : ((K * (M + 1) + 1) & ~1);      // compile-time without covariates
-      rows.run(a.P4, [&](int p, const double (&c)[V]) {
+      auto row = [&](int p, const double (&c)[V]) {
         cf.load(g + p * QSc, a.D, st.x);
 #pragma unroll
         for (int v = 0; v < V; v++) {
@@ -498,7 +527,8 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
           so[v] = fma(ro, ro, so[v]);
           sn[v] = fma(rn, rn, sn[v]);
         }
-      });
+      };
+      rows.run(a.P4, row);
     } else {
       constexpr int NB = BWMAX;
       BandWin wo[V], wn[V];
@@ -558,6 +588,31 @@ __global__ void __launch_bounds__(PF_THREADS, (V == 1 && !RG) ? BF_Z_MINB : 4) z
     }
   }
   grid_reduce<K + 1>(red, a);
+}
+
+// The proposal half of the Z step on its own (z_propose above): reads Z, writes (z*[K], lr, lu) per function.  It needs
+// neither the globals nor chi nor sigma^2, so the sampler launches it for the NEXT sweep on a side stream while the host
+// draws this sweep's Gaussian blocks; z_kernel<..., PRE = true> then only streams the cache and accepts.
+#ifndef BF_ZP_MINB
+#define BF_ZP_MINB 6
+#endif
+template <int K>
+__global__ void __launch_bounds__(PF_THREADS, BF_ZP_MINB) z_propose_kernel(const PassArgs a) {
+  __shared__ double s_par[10];
+  if (threadIdx.x < 10)
+    s_par[threadIdx.x] = a.zpar_dev ? a.zpar_dev[threadIdx.x] : (threadIdx.x < 8 ? a.pi[threadIdx.x] : (threadIdx.x == 8 ? a.alpha3 : a.sigma_sq));
+  build_log_table();
+  __syncthreads();
+  for (int i = blockIdx.x * PF_THREADS + threadIdx.x; i < a.ld; i += gridDim.x * PF_THREADS) {
+    double z[K], zp[K], lr, lu;
+#pragma unroll
+    for (int k = 0; k < K; k++) z[k] = a.Z[(size_t)k * a.ld + i];
+    z_propose<K>(a, s_par, z, i, zp, lr, lu);
+#pragma unroll
+    for (int k = 0; k < K; k++) a.zprop_out[(size_t)k * a.ld + i] = zp[k];
+    a.zprop_out[(size_t)K * a.ld + i] = lr;
+    a.zprop_out[(size_t)(K + 1) * a.ld + i] = lu;
+  }
 }
 
 // ================================================================= chi sweep (+ post-update SSR)
@@ -951,7 +1006,7 @@ inline int launch_pass(Kern kern, const PassArgs& a, cudaStream_t s, size_t extr
     const auto key = std::make_pair((const void*)kern, dev);
     auto it = cache.find(key);
     if (it == cache.end() || it->second.first != smem) {
-      if (smem > 48 * 1024) {
+      if (smem > 40 * 1024) {     // dynamic + up to ~6 KB of static shared memory (tables, reduction scratch) must stay within the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
       }

@@ -23,4 +23,37 @@ static int tune_v() { static int v = -1; if (v < 0) { const char* e = std::geten
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s) {
   BF_DISPATCH(z)
 }
+
+// the two halves on their own (see z_propose_kernel)
+#ifndef BF_ZA_V
+#define BF_ZA_V 2
+#endif
+#define BF_CASE_zaccept(KK, MM)                                                                  \
+  case KK * 16 + MM:                                                                             \
+    return cov ? launch_pass<BF_ZA_V>(z_kernel<KK, MM, true, BF_ZA_V, false, true>, a, s)        \
+               : launch_pass<BF_ZA_V>(z_kernel<KK, MM, false, BF_ZA_V, false, true>, a, s);
+int launch_z_accept(const PassArgs& a, int K, int M, cudaStream_t s) {
+  BF_DISPATCH(zaccept)
+}
+// Blocks of a few grid-stride iterations each, not one resident wave: the kernel usually runs on the low-priority side
+// stream beside the sweep's own kernels, and short blocks hand their slots back to those as they finish.
+template <int K>
+static int launch_propose(const PassArgs& a, cudaStream_t s) {
+  constexpr int ITER = 3;
+  int grid = (a.ld + PF_THREADS * ITER - 1) / (PF_THREADS * ITER);
+  if (grid < 1) grid = 1;
+  z_propose_kernel<K><<<grid, PF_THREADS, 0, s>>>(a);
+  g_launch_count++;
+  return (int)cudaGetLastError();
+}
+int launch_z_propose(const PassArgs& a, int K, cudaStream_t s) {
+  switch (K) {
+    case 2: return launch_propose<2>(a, s);
+    case 3: return launch_propose<3>(a, s);
+    case 4: return launch_propose<4>(a, s);
+    case 5: return launch_propose<5>(a, s);
+    case 6: return launch_propose<6>(a, s);
+    default: return -2;
+  }
+}
 }  // namespace bf

@@ -272,6 +272,11 @@ class Engine:
         self._chk(self._lib.bfmmm_debug_update_chi_rng(self._h, C.c_double(beta), _p(eps)))
         return eps
 
+    def debug_z_propose(self, pi, alpha3, a_Z_PM):
+        """The proposal half of the Z step on the engine's stream (kernel timing). False when the step is one kernel."""
+        pi = np.ascontiguousarray(pi, dtype=np.float64)
+        return self._lib.bfmmm_debug_z_propose(self._h, _p(pi), C.c_double(alpha3), C.c_double(a_Z_PM)) == 0
+
     def debug_moments_valid(self):
         """True when the next update_chi draws from the moments the preceding ssr() left."""
         return bool(self._lib.bfmmm_debug_moments_valid(self._h))

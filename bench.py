@@ -550,7 +550,16 @@ def run_ours(a):
     g = smp.get()
     pi_now, a3 = g["pi"], g["alpha3"]
     ab = algorithmic_bytes(a, n, eng)
-    kern = {"z_kernel": kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM))}
+    t_z = kernel_ms(lambda: eng.update_z_async(pi_now, a3, hyper.a_Z_PM))
+    if eng.debug_z_propose(pi_now, a3, hyper.a_Z_PM):
+        # the Z step is two kernels: the proposal (reads Z, writes z*, lr, lu; in the sweep it runs ahead of time on a
+        # side stream while the host draws the Gaussian blocks) and the pass over the cache that accepts
+        t_p = kernel_ms(lambda: eng.debug_z_propose(pi_now, a3, hyper.a_Z_PM))
+        kern = {"z_propose_kernel": t_p, "z_kernel": t_z - t_p}
+        ab["z_propose_kernel"] = n * 8 * (2 * K + 2)
+        ab["z_kernel"] += n * 8 * (K + 2)
+    else:
+        kern = {"z_kernel": t_z}
     t_ssr = kernel_ms(lambda: eng.ssr_async())
     if eng.debug_moments_valid():
         # common basis, no covariates: updateSigma's pass leaves the per-function moments and updateChi draws from them

@@ -13,6 +13,9 @@ int bfmmm_debug_get_acc(bfmmm_engine* e, double* acc /* n */);
 int bfmmm_debug_update_z_rng(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta,
                              double* gam_out /* n x K */, double* u_out /* n */);
 int bfmmm_debug_update_chi_rng(bfmmm_engine* e, double beta, double* eps_out /* n x M */);
+/* the proposal half of the Z step (z_propose_kernel) on the engine's stream, for kernel timing; fails when the engine
+ * runs the Z step as one kernel (ragged grids) */
+int bfmmm_debug_z_propose(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM);
 /* 1 when the next bfmmm_update_chi will draw from the per-function moments the preceding bfmmm_ssr left (common basis,
  * no covariates), 0 when it will make its own pass over the cache */
 int bfmmm_debug_moments_valid(bfmmm_engine* e);
