@@ -52,6 +52,17 @@ def library_path() -> str:
     return _LIB
 
 
+def source_hash() -> str:
+    """md5 over the library's sources (csrc/ and include/): identifies the build independently of when it was compiled."""
+    import hashlib
+    h = hashlib.md5()
+    for d in (os.path.join(_HERE, "csrc"), os.path.join(os.path.dirname(_HERE), "include")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
 def build_library(jobs: int = 8, extra: str = "") -> str:
     """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_HERE, "csrc"), f"-j{jobs}", "-s"]

@@ -62,6 +62,8 @@ struct bfmmm_engine {
   double* h_slz_dev = nullptr;
   cudaEvent_t ev_slz = nullptr;
   cudaEvent_t ev_zdone = nullptr, ev_prop = nullptr, ev_queued = nullptr;
+  cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;      // timing events around a proposal kernel on the engine's own stream
+  bool k1_timed = false;
   double prop_pi[8] = {0}, prop_alpha3 = 0, prop_a = 0;
   uint64_t prop_key = 0, prop_iter = 0;
   double *ni = nullptr;                          // ragged grids: points per function (marginal log-likelihood)
@@ -128,6 +130,8 @@ void free_all(bfmmm_engine* e) {
   if (e->ev_zdone) cudaEventDestroy(e->ev_zdone);
   if (e->ev_prop) cudaEventDestroy(e->ev_prop);
   if (e->ev_queued) cudaEventDestroy(e->ev_queued);
+  if (e->ev_k1a) cudaEventDestroy(e->ev_k1a);
+  if (e->ev_k1b) cudaEventDestroy(e->ev_k1b);
   if (e->ev_slz) cudaEventDestroy(e->ev_slz);
   if (e->h_slz) cudaFreeHost(e->h_slz);
   cudaFree(e->Hh); cudaFree(e->Gl); cudaFree(e->rs_partials);
@@ -508,6 +512,13 @@ int bfmmm_get_gram(bfmmm_engine* e, double* G) {
 }
 
 static void z_written(bfmmm_engine* e);
+// BFMMM_DEBUG: reports (and clears) a CUDA error some earlier unchecked call left behind
+static void dbg_stale(const char* where) {
+  static const bool on = std::getenv("BFMMM_DEBUG") != nullptr;
+  if (!on) return;
+  cudaError_t pe = cudaGetLastError();
+  if (pe != cudaSuccess) std::fprintf(stderr, "[bfmmm debug] stale CUDA error at %s: %s\n", where, cudaGetErrorString(pe));
+}
 int bfmmm_set_state(bfmmm_engine* e, const double* Z, const double* chi) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
@@ -656,12 +667,15 @@ static int z_split_init(bfmmm_engine* e) {
   CU(cudaEventCreateWithFlags(&e->ev_slz, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_zdone, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_queued, cudaEventDisableTiming));
+  CU(cudaEventCreate(&e->ev_k1a));
+  CU(cudaEventCreate(&e->ev_k1b));
   CU(cudaEventCreateWithFlags(&e->ev_prop, cudaEventDisableTiming));
   return 0;
 }
 
 static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z_PM, double beta, bool injected,
                     bool dump_draws, const double* zpar_dev = nullptr) {
+  dbg_stale("z_launch entry");
   bf::PassArgs a;
   fill_pass(e, a, beta);
   e->mom_valid = false;
@@ -686,8 +700,11 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
     } else {
       CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));          // a stale proposal may still be writing the buffer
       a.zprop_out = e->zprop;
+      CU(cudaEventRecord(e->ev_k1a, e->stream));
       rc = bf::launch_z_propose(a, e->K, e->stream);
       if (rc) return fail("z proposal kernel launch failed rc=" + std::to_string(rc));
+      CU(cudaEventRecord(e->ev_k1b, e->stream));
+      e->k1_timed = true;
     }
     a.zprop = e->zprop; a.zprop_out = nullptr;
     a.gam = nullptr; a.u = nullptr; a.draws_out = nullptr;
@@ -697,6 +714,7 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
     rc = e->ragged ? bf::launch_z_ragged(a, e->K, e->M, e->stream) : bf::launch_z(a, e->K, e->M, e->stream);
   }
   if (rc) return fail("z kernel launch failed rc=" + std::to_string(rc));
+  dbg_stale("z_launch exit");
   return 0;
 }
 
@@ -873,13 +891,14 @@ int bfmmm_sigma_wait(bfmmm_engine* e, double* ssr, double* sigma_sq) {
 int bfmmm_suffstats_async(bfmmm_engine* e) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
+  dbg_stale("suffstats entry");
   bf::StatsArgs a;
   a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.K = e->K; a.M = e->M; a.D = e->D; a.q = e->q;
   a.tma = (!e->ragged && e->tma.valid) ? &e->tma : nullptr;
   a.Ct = e->ragged ? e->Hh : e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
   a.WtW = e->stats + e->off_wtw(); a.CtW = e->stats + e->off_ctw(); a.blocks = e->st_blocks;
   int rc = bf::launch_stats(a, e->stream);
-  if (rc) return fail("stats kernel launch failed rc=" + std::to_string(rc));
+  if (rc) return fail("stats kernel launch failed rc=" + std::to_string(rc) + " (" + cudaGetErrorString((cudaError_t)rc) + ")");
   if (e->ragged) {
     bf::RaggedStatsArgs r;
     r.n = e->n; r.ld = e->ld; r.P = e->P; r.bw = e->bw; r.K = e->K; r.M = e->M; r.D = e->D; r.q = e->q; r.npairs = e->npairs;
@@ -1096,10 +1115,12 @@ int bfmmm_z_propose_async(bfmmm_engine* e, const double* pi, double alpha3, doub
 // the sums must go through the exchange first.
 int bfmmm_slz_read_begin(bfmmm_engine* e) {
   if (!e) return fail("null engine");
+  dbg_stale("slz_read_begin entry");
   CU(cudaSetDevice(e->device));
   if (z_split_init(e)) return 1;
   if (bf::launch_copy_to_host(e->stats + e->off_slz(), e->h_slz_dev, e->K + 1, e->stream)) return fail("copy_to_host kernel launch failed");
   CU(cudaEventRecord(e->ev_slz, e->stream));
+  dbg_stale("slz_read_begin exit");
   return 0;
 }
 int bfmmm_slz_read_wait(bfmmm_engine* e, double* out) {
@@ -1110,6 +1131,21 @@ int bfmmm_slz_read_wait(bfmmm_engine* e, double* out) {
   return 0;
 }
 bool bfmmm_z_ahead_supported(bfmmm_engine* e) { return e && e->z_split; }
+// duration in microseconds of the last proposal kernel that ran on the engine's own stream (alone, in front of its accept
+// kernel), or a negative value when none has finished yet: what the sampler weighs against its own block-draw time
+double bfmmm_z_propose_us(bfmmm_engine* e) {
+  if (!e || !e->k1_timed) return -1.0;
+  cudaSetDevice(e->device);
+  float ms = 0;
+  cudaError_t rc = cudaEventQuery(e->ev_k1b);
+  if (rc == cudaSuccess) rc = cudaEventElapsedTime(&ms, e->ev_k1a, e->ev_k1b);
+  if (rc != cudaSuccess) {
+    if (rc != cudaErrorNotReady && std::getenv("BFMMM_DEBUG")) std::fprintf(stderr, "bfmmm_z_propose_us: %s\n", cudaGetErrorString(rc));
+    cudaGetLastError();          // not an error of the sweep: do not leave it for the next launch check to find
+    return -1.0;
+  }
+  return 1e3 * ms;
+}
 void bfmmm_moments_invalidate(bfmmm_engine* e) { if (e) e->mom_valid = false; }
 // Z step with pi, alpha_3 and sigma^2 read from device memory ([pi (8) | alpha_3 | sigma^2])
 int bfmmm_update_z_async_p(bfmmm_engine* e, double a_Z_PM, double beta, const double* zpar_dev) {

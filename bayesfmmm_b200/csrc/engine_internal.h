@@ -26,3 +26,4 @@ int bfmmm_z_propose_async(bfmmm_engine* e, const double* pi, double alpha3, doub
 int bfmmm_slz_read_begin(bfmmm_engine* e);
 int bfmmm_slz_read_wait(bfmmm_engine* e, double* out /* K + 1 */);
 bool bfmmm_z_ahead_supported(bfmmm_engine* e);     // the Z step runs as proposal + accept kernels (common basis)
+double bfmmm_z_propose_us(bfmmm_engine* e);        // last proposal kernel timed alone on the engine's stream (< 0: none yet)

@@ -18,6 +18,9 @@
 
 #include "common.cuh"
 #include "globals_core.cuh"
+#include <mutex>
+#include <set>
+
 #include "globals_dev.h"
 
 namespace bf {
@@ -285,10 +288,16 @@ size_t draw_blocks_smem(const DrawArgs& a) {
 int launch_draw_blocks(const DrawArgs& a, cudaStream_t s) {
   if (a.hbmax > 0 && a.g.P > DB_PMAX - 2) return 2;
   const size_t smem = draw_blocks_smem(a);
-  static bool configured = false;
-  if (smem > 48 * 1024 && !configured) {
-    if (cudaFuncSetAttribute(draw_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1;
-    configured = true;
+  if (smem > 48 * 1024) {               // once per device (the attribute is per context)
+    static std::set<int> configured;
+    static std::mutex configured_mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(configured_mu);
+    if (!configured.count(dev)) {
+      if (cudaFuncSetAttribute(draw_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 1;
+      configured.insert(dev);
+    }
   }
   draw_blocks_kernel<<<1, DB_THREADS, smem, s>>>(a);
   g_launch_count++;

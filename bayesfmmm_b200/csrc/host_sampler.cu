@@ -202,6 +202,7 @@ struct bfmmm_sampler {
   vecd stats;     // host copy of the engine statistics buffer
   vecd tt_ssr, tt_sigma;   // per-slot trace of the last tempered transition
   double last_ssr = 0;     // SSR of the state the last sweep ended with
+  double z_k1_us = -1, z_blocks_us = -1;   // Z proposal kernel alone / the host's Phi + nu block draws (microseconds)
   // The SSR after the chi step only feeds the reported log-likelihood, never the chain: its read-back
   // (and, on several GPUs, its all-reduce) is folded into the NEXT sweep's first exchange.
   bool ll_pending = false;
@@ -1382,8 +1383,19 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   // queued on a side stream as soon as pi and alpha_3 are known and runs beside the statistics kernel and the host's
   // Gaussian block draws.  pi and alpha_3 draw from their own Philox streams, so taking them first changes nothing
   // unless the draws come from a tape (then the reference's order is kept and nothing runs ahead).
-  static const bool z_ahead_on = !std::getenv("BFMMM_NO_Z_AHEAD");
-  const bool z_ahead = do_z && !s->rng.use_tape && z_ahead_on && bfmmm_z_ahead_supported(e);
+  // It pays when the gap in which the device would idle (the host's block draws plus ~25 us of read-back, push and launch
+  // latency) is about as long as the proposal kernel; with quick block draws (identity basis) the kernel would only be
+  // pushed behind the SSR pass by the stream
+  // priorities and the Z step would wait for it, so it then stays in front of its accept kernel.  Both times are
+  // measured: the first sweep's proposal runs alone on the engine's stream (timed by events), the block draws by the clock.
+  static const bool z_ahead_on = !std::getenv("BFMMM_NO_Z_AHEAD"), z_ahead_always = std::getenv("BFMMM_Z_AHEAD_ALWAYS") != nullptr;
+  {
+    // the shortest of the timings seen: the first launch of a kernel also waits for its module to load
+    const double t = bfmmm_z_propose_us(e);
+    if (t >= 0 && (s->z_k1_us < 0 || t < s->z_k1_us)) s->z_k1_us = t;
+  }
+  const bool worth = z_ahead_always || (s->z_k1_us >= 0 && s->z_blocks_us >= 0 && s->z_blocks_us + 25.0 >= 0.7 * s->z_k1_us);
+  const bool z_ahead = do_z && !s->rng.use_tape && z_ahead_on && worth && bfmmm_z_ahead_supported(e);
   const bool z_early = z_ahead && !s->allreduce;           // one shard: sum_i log Z_ik needs no exchange
   if (do_z) {                                              // updateZ_PM -> updatePi_PM -> updateAlpha3
     if (bfmmm_update_z_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, beta)) return 1;
@@ -1432,9 +1444,14 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
     if (bfmmm_z_propose_async(e, s->pi.data(), s->alpha3, s->h.a_Z_PM, (uint64_t)(s->tick + 1), false)) return 1;
   }
   s->zpre_on = !s->rng.use_tape;
+  const double t_blocks0 = now_s();
   int rc_blocks = (do_phi && bfmmm_host_update_phi(s, st_wtw(s), st_btyw(s), beta)) ||   // updatePhi
                   (do_nu && bfmmm_host_update_nu(s, st_wtw(s), st_btyw(s), beta));        // updateNu
   s->zpre_on = false;
+  if (do_phi && do_nu) {
+    const double us = 1e6 * (now_s() - t_blocks0);
+    s->z_blocks_us = s->z_blocks_us < 0 ? us : 0.8 * s->z_blocks_us + 0.2 * us;
+  }
   if (rc_blocks) return 1;
   if (push_globals(s)) return 1;
   if (bfmmm_ssr_async(e)) return 1;                        // updateSigma's data pass, new globals

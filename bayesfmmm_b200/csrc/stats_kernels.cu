@@ -19,6 +19,8 @@
 //   W'W tiles reuse the same registers: A = W' fragment (row = feature, col = slot) == b.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <set>
 #include <utility>
 
@@ -440,11 +442,19 @@ static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& us
   if (smem > (BF_ST_BPS == 2 ? 100 : 64) * 1024) return 0;    // BF_ST_BPS blocks per SM
   int dev = 0;
   cudaGetDevice(&dev);
-  static std::set<std::pair<int, size_t>> configured;       // per device: the attribute is per context
-  if (!configured.count({dev, smem})) {
-    cudaError_t e = cudaFuncSetAttribute(stats_kernel_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured.insert({dev, smem});
+  // The attribute is one value per (kernel, device) and the stage size depends on K, M, D, not only on <MT, NT>: it is
+  // raised when an engine needs more than any before it (a set of the sizes seen would let a smaller engine lower it
+  // under a larger one created earlier).  Several host threads may drive several engines: locked.
+  static std::map<int, size_t> granted;
+  static std::mutex granted_mu;
+  {
+    std::lock_guard<std::mutex> lock(granted_mu);
+    auto it = granted.find(dev);
+    if (it == granted.end() || it->second < smem) {
+      cudaError_t e = cudaFuncSetAttribute(stats_kernel_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      granted[dev] = smem;
+    }
   }
   dim3 grid(a.blocks, gy);
   stats_kernel_tma<MT, NT><<<grid, TM_THREADS, smem, s>>>(a, *a.tma);

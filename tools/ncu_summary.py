@@ -1,7 +1,13 @@
-"""Summarises an ncu launch list (csv) and a `--set full` report into profiles/<tag>_*.{md,json,csv}.
+"""Summarises an ncu launch list (csv) and a `--set full` capture into profiles/<tag>_*.{md,json,csv}.
 
-    python tools/ncu_summary.py <tag> <launches.csv> <report.ncu-rep> [note ...]
+    python tools/ncu_summary.py <tag> <launches.csv> <report.ncu-rep | raw.csv> [workload=nstar] [n=1000000] [note ...]
+
+The capture is either the report itself or its `ncu -i report --page raw --csv` export (a report of the full library
+embeds its 60 MB of cubins and does not fit the 64 MiB that travel back from the GPU box, so the export is made there).
+<tag>_traffic.json is keyed by bench.py's workload and kernel names and carries the md5 of the sources (csrc/, include/) the
+captured library was built from: bench.py reports `roofline.traffic` from it only when its own sources hash to the same.
 """
+import hashlib
 import collections
 import csv
 import json
@@ -15,10 +21,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def main():
     tag, launches, rep = sys.argv[1:4]
-    notes = sys.argv[4:]
+    rest = sys.argv[4:]
+    workload = next((a.split("=", 1)[1] for a in rest if a.startswith("workload=")), "nstar")
+    n_per_gpu = int(next((a.split("=", 1)[1] for a in rest if a.startswith("n=")), "1000000"))
+    notes = [a for a in rest if not a.startswith(("workload=", "n="))]
     out_dir = os.path.join(ROOT, "profiles")
     os.makedirs(out_dir, exist_ok=True)
-    shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches.csv"))
+    if os.path.abspath(launches) != os.path.abspath(os.path.join(out_dir, f"{tag}_launches.csv")):
+        shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches.csv"))
     rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
     for i, r in enumerate(rows):
         if "Kernel Name" in r:
@@ -34,7 +44,7 @@ def main():
     tot = sum(sum(v) for v in agg.values())
     sweep = [k for k in agg if "project" not in k and "bspline" not in k and "prep" not in k]
     tsweep = sum(sum(agg[k]) for k in sweep)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     h = rr[0]
 
@@ -62,8 +72,9 @@ def main():
         rd, wr = float(col(r, "dram__bytes_read.sum")), float(col(r, "dram__bytes_write.sum"))
         unit = rr[1][h.index("dram__bytes_read.sum")]
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1e6)
-        short = k.replace("void ", "").split("<")[0]
-        traffic[short] = (rd + wr) * scale
+        short = k.replace("void ", "").replace("bf::", "").split("<")[0]
+        short = {"stats_kernel_tma": "stats_kernels", "ragged_stats_kernel": "ragged_stats_kernel"}.get(short, short)
+        traffic[short] = traffic.get(short, 0.0) + (rd + wr) * scale
         L.append(f"| `{k}` | {float(col(r, 'gpu__time_duration.sum')):.1f} | {rd * scale / 1e6:.1f} | {wr * scale / 1e6:.1f} | "
                  f"{float(col(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
                  f"{float(col(r, 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')):.1f} | "
@@ -72,8 +83,13 @@ def main():
                  f"{float(col(r, 'sm__warps_active.avg.pct_of_peak_sustained_active')):.1f} | "
                  f"{col(r, 'launch__registers_per_thread')} | {float(col(r, 'smsp__inst_executed.sum')) / 1e6:.1f} M |")
     open(os.path.join(out_dir, f"{tag}_ncu_summary.md"), "w").write("\n".join(L) + "\n")
-    json.dump({"unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
-               "n_per_gpu": 1000000, "kernels": traffic}, open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1)
+    sys.path.insert(0, ROOT)
+    from bayesfmmm_b200 import _lib
+    path = os.path.join(out_dir, f"{tag}_traffic.json")
+    doc = json.load(open(path)) if os.path.exists(path) else {}
+    doc["unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, first launch of each kernel)"
+    doc[workload] = {"n_per_gpu": n_per_gpu, "source_md5": _lib.source_hash(), "kernels": traffic}
+    json.dump(doc, open(path, "w"), indent=1)
     print("\n".join(L[-8:]))
 
 
