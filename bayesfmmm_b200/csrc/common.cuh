@@ -355,7 +355,6 @@ int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots,
 int launch_copy_to_host(const double* src, double* dst_mapped, int64_t len, cudaStream_t s);   // SM-driven D2H of a few KB
 int launch_sigma_draw(const double* ssr_dev, double a, double scale_ssr, double beta0, uint64_t key, uint64_t iteration,
                       uint32_t purpose, double* sigma_dev, double* host_mapped, double seq, cudaStream_t s);
-int launch_log_rows(const double* src, double* dst, size_t count, cudaStream_t s);   // dst = log(src), elementwise
 
 extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library (all engines, all host threads)
 int set_error(const char* msg);   // records the message returned by bfmmm_last_error(); returns 1

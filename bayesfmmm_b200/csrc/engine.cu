@@ -64,6 +64,7 @@ struct bfmmm_engine {
   cudaEvent_t ev_zdone = nullptr, ev_prop = nullptr, ev_queued = nullptr;
   cudaEvent_t ev_k1a = nullptr, ev_k1b = nullptr;      // timing events around a proposal kernel on the engine's own stream
   bool k1_timed = false;
+  long long n_prop_ahead = 0, n_prop_own = 0;     // Z steps that used an ahead-of-time proposal / made their own
   double prop_pi[8] = {0}, prop_alpha3 = 0, prop_a = 0;
   uint64_t prop_key = 0, prop_iter = 0;
   double *ni = nullptr;                          // ragged grids: points per function (marginal log-likelihood)
@@ -403,12 +404,17 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
     if (_e != cudaSuccess) { fail(std::string(#x) + ": " + cudaGetErrorString(_e)); return bail(1); } \
   } while (0)
   {
-    // the engine's stream outranks its side stream (ahead-of-time Z proposals): when both have blocks to place, the
-    // sweep's own kernels go first
+    // Stream priorities: the side stream (ahead-of-time Z proposals, z_propose_kernel) OUTRANKS the engine's stream.  The
+    // proposal is launched into the gap in which the device waits for the host's block draws; when the SSR pass arrives
+    // before it has finished, its remaining blocks go first and the pass then runs undisturbed.  The other way round the
+    // persistent SSR pass takes the SMs as the proposal's blocks retire, the proposal finishes behind it and the next Z
+    // step waits (measured on 2 GPUs: no gain at all from running ahead).  BFMMM_SIDE_PRIO=low restores that order.
     int least = 0, greatest = 0;
     CUE(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    e->prio_side = least;
-    CUE(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, greatest));
+    const char* pr = std::getenv("BFMMM_SIDE_PRIO");
+    const bool side_low = pr && pr[0] == 'l';
+    e->prio_side = side_low ? least : greatest;
+    CUE(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, side_low ? greatest : least));
   }
   const size_t ld = e->ld;
   e->P4 = (e->P + 3) & ~3;
@@ -485,7 +491,11 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   return 0;
 }
 
-void bfmmm_destroy(bfmmm_engine* e) { free_all(e); }
+void bfmmm_destroy(bfmmm_engine* e) {
+  if (e && std::getenv("BFMMM_DEBUG") && (e->n_prop_ahead || e->n_prop_own))
+    std::fprintf(stderr, "[bfmmm debug] Z steps: %lld with an ahead-of-time proposal, %lld with their own\n", e->n_prop_ahead, e->n_prop_own);
+  free_all(e);
+}
 
 int bfmmm_get_basis(bfmmm_engine* e, double* B_out) {
   if (!e || e->identity) return fail("bfmmm_get_basis: no basis for this model");
@@ -696,9 +706,11 @@ static int z_launch(bfmmm_engine* e, const double* pi, double alpha3, double a_Z
     for (int k = 0; ahead && k < e->K; k++) ahead = (e->prop_pi[k] == pi[k]);
     e->prop_valid = false;
     if (ahead) {
+      e->n_prop_ahead++;
       CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));          // made ahead of time on the side stream
     } else {
       CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));          // a stale proposal may still be writing the buffer
+      e->n_prop_own++;
       a.zprop_out = e->zprop;
       CU(cudaEventRecord(e->ev_k1a, e->stream));
       rc = bf::launch_z_propose(a, e->K, e->stream);
@@ -1057,7 +1069,9 @@ int bfmmm_debug_z_propose(bfmmm_engine* e, const double* pi, double alpha3, doub
   e->prop_valid = false;
   CU(cudaStreamWaitEvent(e->stream, e->ev_prop, 0));
   a.zprop_out = e->zprop;
+  CU(cudaEventRecord(e->ev_k1a, e->stream));          // the same event records as in the Z step, so that their cost
   if (bf::launch_z_propose(a, e->K, e->stream)) return fail("z proposal kernel launch failed");
+  CU(cudaEventRecord(e->ev_k1b, e->stream));          // cancels in (whole step) - (this call)
   return 0;
 }
 // 1 when the next bfmmm_update_chi will draw from the moments the last SSR pass left (moments_kernels.cu)

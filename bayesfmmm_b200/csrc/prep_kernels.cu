@@ -43,22 +43,6 @@ int launch_bspline(const double* t, int64_t n, const double* knots, int n_knots,
   return (int)cudaGetLastError();
 }
 
-// ------------------------------------------------------------------ log Z cache
-// dst = log(src): the Z step keeps log Z next to Z (the logs of the current state are then read, not
-// recomputed, every iteration); this kernel initialises the cache when the caller sets Z.
-__global__ void __launch_bounds__(256) log_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, size_t count) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = log(src[i]);
-}
-int launch_log_rows(const double* src, double* dst, size_t count, cudaStream_t s) {
-  if (count == 0) return 0;
-  size_t blocks = (count + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  log_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, count);
-  g_launch_count++;
-  return (int)cudaGetLastError();
-}
-
 // ------------------------------------------------------------------ statistics read-back without a copy engine
 // The sampler reads a few KB of reduced statistics two or three times per sweep.  As cudaMemcpyAsync
 // those reads queue on the device-to-host copy engine behind an overlapped 48 MB state transfer

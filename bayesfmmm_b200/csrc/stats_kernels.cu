@@ -422,10 +422,14 @@ static int launch_stats_x(const StatsArgs& a, int gy, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   static std::set<int> configured;                            // per device: the attribute is per context
-  if (!configured.count(dev)) {
-    cudaError_t e = cudaFuncSetAttribute(stats_kernel<MT, NT, ST, HASX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured.insert(dev);
+  static std::mutex configured_mu;                            // (several host threads may drive several engines)
+  {
+    std::lock_guard<std::mutex> lock(configured_mu);
+    if (!configured.count(dev)) {
+      cudaError_t e = cudaFuncSetAttribute(stats_kernel<MT, NT, ST, HASX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured.insert(dev);
+    }
   }
   stats_kernel<MT, NT, ST, HASX><<<grid, ST_THREADS, smem, s>>>(a);
   return 0;
