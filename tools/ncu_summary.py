@@ -51,9 +51,10 @@ def main():
     def col(r, n):
         return r[h.index(n)] if n in h else "nan"
     L = [f"# {tag}: ncu summary (B200, sm_100a)", "",
-         "Commands (each after the same command line exited 0 without ncu):", "",
-         "    ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
-         "    ncu --set full --clock-control none --import-source on -k regex:'z_kernel|chi_kernel|ssr_kernel|stats_kernel' -s 20 -c 8 -o prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline",
+         "Commands: `tools/evidence.sh` (each ncu pass only after the same `python bench.py --workload " + workload +
+         " --steps 3 --warmup 3 --no-cpu-baseline --no-extras` had exited 0 without ncu):", "",
+         "    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file launches.csv <bench command>",
+         "    ncu --set full --clock-control none -k regex:'<the sweep's kernels>' -s <skip> -c 12 -o full <bench command>; ncu -i full.ncu-rep --page raw --csv",
          ""] + notes + ["",
          "## Launch list: share of device time (per-launch times are cold-cache and serialised: compare shares)", "",
          "| kernel | launches | avg us | share of all | share of the sweep |", "|---|---|---|---|---|"]
