@@ -299,8 +299,21 @@ struct alignas(64) StatsTmaMaps {
   CUtensorMap ct, z, chi, x;
   int valid, mt;
 };
+// One-shot exchange over NVLink peer memory (p2p_hook.cu): every rank owns a mailbox in its HBM, mapped into its peers.
+constexpr int P2P_MAX_RANKS = 16;
+constexpr size_t P2P_HDR = 256;     // flags[P2P_MAX_RANKS] (sequence number last published by each rank), then data[2][world][cap]
+struct P2PPeers { unsigned char* box[P2P_MAX_RANKS]; };
+// what the statistics pass's final-reduction kernel does with the reduced buffer besides leaving it in `stats`
+struct StatsEpilogue {
+  double* stats;                // device statistics buffer [header (hdr) | W'W | C~'W]
+  double* mirror;               // device alias of the mapped page-locked host copy (nullptr: none)
+  int hdr;                      // header slots [sum log Z (K) | accepts | ssr | ssr_after]
+  unsigned* ticket;             // blocks-done counter (exchange only)
+  P2PPeers peers; int rank, world, cap; unsigned long long seq;     // world <= 1: no exchange
+};
 struct StatsArgs {
   int n, ld, P, K, M, D, q;
+  StatsEpilogue ep;
   const StatsTmaMaps* tma;          // host pointer (passed to the kernel by value) or nullptr
   const double* __restrict__ Ct;
   const double* __restrict__ Z;

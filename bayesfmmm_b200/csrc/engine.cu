@@ -87,6 +87,12 @@ struct bfmmm_engine {
   int stage_next = 0;
   double* h_stats = nullptr;
   double* h_stats_dev = nullptr;   // device alias of h_stats (mapped page-locked memory)
+  bool mirror_valid = false;       // h_stats holds the whole reduced buffer (stored by the statistics pass's epilogue)
+  bool stats_exchanged = false;    // ... and that epilogue already summed it over the shards
+  unsigned int* st_ticket = nullptr;
+  bool xchg_on = false;            // peer-memory exchange fused into the statistics pass's epilogue (bfmmm_engine_set_exchange)
+  bf::P2PPeers xchg_peers; int xchg_rank = 0, xchg_world = 1, xchg_cap = 0;
+  unsigned long long* xchg_seq = nullptr;
   double *sigma_dev = nullptr, *h_sig = nullptr, *h_sig_dev = nullptr;   // device-drawn sigma^2; mapped {SSR, sigma^2, seq}
   double sig_seq = 0;
   bool sigma_armed = false;        // the next chi kernel reads sigma^2 from sigma_dev
@@ -125,7 +131,7 @@ void free_all(bfmmm_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaFree(e->Ct); cudaFree(e->rss); cudaFree(e->Z); cudaFree(e->chi); cudaFree(e->X); cudaFree(e->glob);
-  cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket);
+  cudaFree(e->draws); cudaFree(e->stats); cudaFree(e->partials); cudaFree(e->st_partials); cudaFree(e->ticket); cudaFree(e->st_ticket);
   cudaFree(e->acc_dbg); cudaFree(e->snapZ); cudaFree(e->snapChi); cudaFree(e->mom); cudaFree(e->zprop);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_zdone) cudaEventDestroy(e->ev_zdone);
@@ -434,6 +440,8 @@ int bfmmm_create(const bfmmm_config* c, bfmmm_engine** out) {
   CUE(cudaMalloc(&e->st_partials, bf::stats_partial_doubles(e->P, e->q, e->st_blocks) * 8));
   CUE(cudaMalloc(&e->ticket, 4));
   CUE(cudaMemsetAsync(e->ticket, 0, 4, e->stream));
+  CUE(cudaMalloc(&e->st_ticket, 4));
+  CUE(cudaMemsetAsync(e->st_ticket, 0, 4, e->stream));
   CUE(cudaMemsetAsync(e->Ct, 0, ld * e->P4 * 8, e->stream));
   CUE(cudaMemsetAsync(e->rss, 0, ld * 8, e->stream));
   CUE(cudaMemsetAsync(e->Z, 0, ld * e->K * 8, e->stream));
@@ -636,6 +644,7 @@ int bfmmm_set_globals(bfmmm_engine* e, const double* nu, const double* Phi, cons
 
 static void fill_pass(bfmmm_engine* e, bf::PassArgs& a, double beta) {
   std::memset(&a, 0, sizeof(a));
+  e->mirror_valid = false; e->stats_exchanged = false;      // every pass kernel writes a slot of the statistics header
   a.n = e->n; a.ld = e->ld; a.P = e->Pc; a.D = e->D; a.QS = e->QS; a.P4 = (e->Pc + 3) & ~3;
   a.sm_count = e->sm_count; a.max_blocks = e->pass_blocks;
   a.Ct = e->Ct; a.Gl = e->Gl; a.bw = e->bw; a.rss = e->rss; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.glob = e->glob;
@@ -909,8 +918,26 @@ int bfmmm_suffstats_async(bfmmm_engine* e) {
   a.tma = (!e->ragged && e->tma.valid) ? &e->tma : nullptr;
   a.Ct = e->ragged ? e->Hh : e->Ct; a.Z = e->Z; a.chi = e->chi; a.X = e->X; a.partials = e->st_partials;
   a.WtW = e->stats + e->off_wtw(); a.CtW = e->stats + e->off_ctw(); a.blocks = e->st_blocks;
+  // Epilogue of the final reduction.  On several GPUs with the peer-memory exchange installed, the last block of the
+  // final reduction exchanges the buffer and stores the totals into the mapped host copy (one launch instead of three).
+  // On one GPU the same trick (BFMMM_STATS_EPILOGUE=1) was measured SLOWER than the separate copy kernel (0.277 against
+  // 0.273 ms per sweep: fence + ticket + a serial tail block cost more than a kernel boundary), so it is off.
+  // Ragged grids append the pair cross-Gram band behind this pass: they keep the separate exchange and read-back.
+  static const bool no_epilogue = std::getenv("BFMMM_NO_STATS_EPILOGUE") != nullptr;
+  static const bool mirror_always = std::getenv("BFMMM_STATS_EPILOGUE") != nullptr;
+  std::memset(&a.ep, 0, sizeof(a.ep));
+  a.ep.stats = e->stats; a.ep.hdr = e->K + 3; a.ep.ticket = e->st_ticket; a.ep.world = 1;
+  const bool epilogue = !e->ragged && !no_epilogue && (e->xchg_on || mirror_always);
+  if (epilogue) a.ep.mirror = e->h_stats_dev;
+  const bool exchange = epilogue && e->xchg_on;
+  if (exchange) {
+    a.ep.peers = e->xchg_peers; a.ep.rank = e->xchg_rank; a.ep.world = e->xchg_world; a.ep.cap = e->xchg_cap;
+    a.ep.seq = ++*e->xchg_seq;
+  }
+  e->mirror_valid = false; e->stats_exchanged = false;
   int rc = bf::launch_stats(a, e->stream);
   if (rc) return fail("stats kernel launch failed rc=" + std::to_string(rc) + " (" + cudaGetErrorString((cudaError_t)rc) + ")");
+  e->mirror_valid = epilogue; e->stats_exchanged = exchange;
   if (e->ragged) {
     bf::RaggedStatsArgs r;
     r.n = e->n; r.ld = e->ld; r.P = e->P; r.bw = e->bw; r.K = e->K; r.M = e->M; r.D = e->D; r.q = e->q; r.npairs = e->npairs;
@@ -982,6 +1009,7 @@ int bfmmm_suffstats_ragged(bfmmm_engine* e, double* WtW, double* BtYW, double* H
 int bfmmm_clear_ssr_after(bfmmm_engine* e) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
+  e->mirror_valid = false;
   CU(cudaMemsetAsync(e->stats + e->off_ssr_after(), 0, 8, e->stream));
   return 0;
 }
@@ -995,14 +1023,17 @@ int bfmmm_seed(bfmmm_engine* e, uint64_t key, uint64_t iteration) {
 int bfmmm_stats_buffer_dev(bfmmm_engine* e, double** ptr, int64_t* len) {
   if (!e) return fail("null engine");
   *ptr = e->stats; *len = e->stats_len;
+  e->mirror_valid = false;         // the caller may change the buffer (all-reduce hooks do)
   return 0;
 }
 int bfmmm_read_stats(bfmmm_engine* e, double* out, int64_t len) {
   if (!e) return fail("null engine");
   CU(cudaSetDevice(e->device));
   if (len > e->stats_len) len = e->stats_len;
-  // SM-driven store into mapped host memory: does not queue behind an overlapped state transfer
-  if (bf::launch_copy_to_host(e->stats, e->h_stats_dev, len, e->stream)) return fail("copy_to_host kernel launch failed");
+  // SM-driven store into mapped host memory: does not queue behind an overlapped state transfer (the statistics pass's
+  // epilogue has already stored the buffer there when nothing has touched it since)
+  if (!e->mirror_valid && bf::launch_copy_to_host(e->stats, e->h_stats_dev, len, e->stream)) return fail("copy_to_host kernel launch failed");
+  e->mirror_valid = false;         // the C~'W block is un-whitened in place below
   CU(cudaStreamSynchronize(e->stream));
   // the C~'W block is returned un-whitened (B'Y'W), like bfmmm_suffstats
   std::vector<double> tmp;
@@ -1089,6 +1120,20 @@ int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
 }  // extern "C"
 
 // ---- internal entry points of the device-resident sweep (engine_internal.h; not part of the C ABI)
+int64_t bfmmm_stats_len(bfmmm_engine* e) { return e ? e->stats_len : 0; }
+// 1 when the statistics pass queued last already summed the whole buffer over the shards in its epilogue
+int bfmmm_stats_exchanged(bfmmm_engine* e) { return e && e->stats_exchanged ? 1 : 0; }
+// Fuses the peer-memory exchange (p2p_hook.cu's mailboxes and sequence counter) into the statistics pass's epilogue.
+int bfmmm_engine_set_exchange(bfmmm_engine* e, const bf::P2PPeers* peers, int rank, int world, int cap, unsigned long long* seq) {
+  if (!e) return fail("null engine");
+  if (!peers || world < 2) { e->xchg_on = false; return 0; }
+  if (world > bf::P2P_MAX_RANKS || rank < 0 || rank >= world || !seq) return fail("bfmmm_engine_set_exchange: bad argument");
+  if (e->ragged) { e->xchg_on = false; return 0; }
+  if (cap < e->K + 3 + e->q * e->q + e->P * e->q) return fail("bfmmm_engine_set_exchange: mailbox slots shorter than the statistics buffer");
+  e->xchg_peers = *peers; e->xchg_rank = rank; e->xchg_world = world; e->xchg_cap = cap; e->xchg_seq = seq;
+  e->xchg_on = !std::getenv("BFMMM_NO_FUSED_EXCHANGE");
+  return 0;
+}
 int bfmmm_engine_devinfo(bfmmm_engine* e, bf::EngineDevInfo* o) {
   if (!e || !o) return fail("null argument");
   o->stats = e->stats; o->glob = e->glob; o->Pc = e->Pc; o->P4 = (e->Pc + 3) & ~3; o->QS = e->QS; o->hbL = e->hbL;

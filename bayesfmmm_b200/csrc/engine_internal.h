@@ -7,6 +7,7 @@
 #include "../../include/bfmmm.h"
 
 namespace bf {
+struct P2PPeers;
 struct EngineDevInfo {
   double* stats;          // device statistics buffer [sum log Z (K) | accepts | ssr | ssr_after | W'W | C~'W ...]
   int64_t stats_len;
@@ -27,3 +28,7 @@ int bfmmm_slz_read_begin(bfmmm_engine* e);
 int bfmmm_slz_read_wait(bfmmm_engine* e, double* out /* K + 1 */);
 bool bfmmm_z_ahead_supported(bfmmm_engine* e);     // the Z step runs as proposal + accept kernels (common basis)
 double bfmmm_z_propose_us(bfmmm_engine* e);        // last proposal kernel timed alone on the engine's stream (< 0: none yet)
+// peer-memory exchange fused into the statistics pass's final reduction (csrc/p2p_hook.cu installs it)
+int bfmmm_engine_set_exchange(bfmmm_engine* e, const bf::P2PPeers* peers, int rank, int world, int cap, unsigned long long* seq);
+int bfmmm_stats_exchanged(bfmmm_engine* e);        // the statistics pass queued last summed the buffer over the shards itself
+int64_t bfmmm_stats_len(bfmmm_engine* e);          // doubles in the statistics buffer

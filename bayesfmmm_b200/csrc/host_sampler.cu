@@ -257,6 +257,8 @@ struct bfmmm_sampler {
   int feat(int k, int mm, int dd) const { return (k * (M + 1) + mm) * (1 + D) + dd; }
 };
 
+bfmmm_engine* bfmmm_sampler_engine(bfmmm_sampler* s) { return s ? s->e : nullptr; }
+
 namespace {
 
 // an update that asked for more injected draws than the tape held has produced NaNs: fail instead of returning them
@@ -576,8 +578,11 @@ int push_globals(bfmmm_sampler* s) {
 int reduce_and_read(bfmmm_sampler* s, bool only_ssr = false) {
   struct T { bfmmm_sampler* s; double t0; ~T() { s->t_wait += now_s() - t0; } } timer{s, now_s()};
   double* dev = nullptr; int64_t len = 0;
-  if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
-  if (s->allreduce) {
+  // the statistics pass may have summed the whole buffer over the shards in its own epilogue (peer-memory exchange)
+  const bool exchanged = !only_ssr && bfmmm_stats_exchanged(s->e);
+  if (exchanged || !s->allreduce) len = bfmmm_stats_len(s->e);      // nobody touches the buffer: the epilogue's host copy stands
+  else if (bfmmm_stats_buffer_dev(s->e, &dev, &len)) return 1;
+  if (s->allreduce && !exchanged) {
     int rc = only_ssr ? s->allreduce(s->allreduce_ctx, dev + s->K + 1, 1, bfmmm_stream(s->e))
                       : s->allreduce(s->allreduce_ctx, dev, len, bfmmm_stream(s->e));
     if (rc) return sfail("all-reduce hook failed");
@@ -790,7 +795,8 @@ int sampler_step_device(bfmmm_sampler* s, int sweep, double beta) {
   if (d.pi_pending) { CUS(cudaStreamWaitEvent(st, d.ev_pi, 0)); d.pi_pending = false; }     // last sweep's pi, alpha_3
   if (do_z && bfmmm_update_z_async_p(e, s->h.a_Z_PM, beta, zpar)) return 1;          // updateZ_PM
   if (bfmmm_suffstats_async(e)) return 1;
-  if (s->allreduce && s->allreduce(s->allreduce_ctx, d.info.stats, d.info.stats_len, st)) return sfail("all-reduce hook failed");
+  if (s->allreduce && !bfmmm_stats_exchanged(e) && s->allreduce(s->allreduce_ctx, d.info.stats, d.info.stats_len, st))
+    return sfail("all-reduce hook failed");
   CUS(cudaEventRecord(d.ev_stats, st));
   // updatePhi, updateNu: the blocks need last sweep's delta, gamma, tau (side stream)
   if (d.priors_pending) { CUS(cudaStreamWaitEvent(st, d.ev_priors, 0)); d.priors_pending = false; }

@@ -17,15 +17,18 @@
 
 #include "../../include/bfmmm_sampler.h"
 #include "common.cuh"
+#include "engine_internal.h"
+
+bfmmm_engine* bfmmm_sampler_engine(bfmmm_sampler* s);      // host_sampler.cu
 
 namespace {
-constexpr int P2P_MAX_RANKS = 16;
+using bf::P2P_MAX_RANKS;
+using bf::P2P_HDR;
 struct Mailbox {                 // layout of one rank's mailbox in its HBM
   unsigned long long flags[P2P_MAX_RANKS];     // sequence number last published by each rank
   // double data[2][world][cap] follows (256-byte aligned)
 };
-constexpr size_t P2P_HDR = 256;
-struct Peers { unsigned char* box[P2P_MAX_RANKS]; };
+typedef bf::P2PPeers Peers;
 
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(double* __restrict__ buf, int len, Peers peers, int rank, int world,
                                                             unsigned long long seq, int cap) {
@@ -120,6 +123,10 @@ int bfmmm_sampler_enable_p2p(bfmmm_sampler* s, void* ctx, const char* handles) {
     c->opened.push_back(p);
     c->peers.box[r] = (unsigned char*)p;
   }
+  // The whole-buffer exchange behind the statistics pass runs inside that pass's final reduction (stats_kernels.cu:
+  // same mailboxes, same sequence counter); the hook below remains for the one-slot exchanges (SSR, log-likelihood).
+  if (bfmmm_engine* e = bfmmm_sampler_engine(s))
+    if (bfmmm_engine_set_exchange(e, &c->peers, c->rank, c->world, c->cap, &c->seq)) return 1;
   return bfmmm_sampler_set_allreduce(s, p2p_allreduce, c);
 }
 

@@ -234,7 +234,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 
 __host__ __device__ inline int tm_align128(int bytes) { return (bytes + 127) & ~127; }
 
-template <int MT, int NT>
+// FOLD (all cache tiles in one block, P % 8 and q % 8 both in 1..4): the last cache tile has at most four real rows and
+// the last feature tile at most four real features, so the remnant features ride in rows 4..7 of the last cache tile's
+// A fragment.  The tiles (MT-1, nt) then carry W'W[remnant][tile nt] in those rows and the NT tiles (n1, NT-1) of W'W
+// are not issued: 7 instead of 9 tiles (14 instead of 18 DMMAs per 8 functions) at P = 20, q = 12.
+template <int MT, int NT, bool FOLD>
 #ifndef BF_ST_BPS
 #define BF_ST_BPS 2      // resident blocks per SM of the statistics kernels (grid = BF_ST_BPS * SM count)
 #endif
@@ -289,6 +293,16 @@ __global__ void __launch_bounds__(TM_THREADS, BF_ST_BPS) stats_kernel_tma(const 
         if (dd > 0) xoff[nt] = off_x + (dd - 1) * TM_STRIDE;
       }
     }
+    int zoffF = -1, coffF = -1, xoffF = -1;  // FOLD: the remnant feature this lane (g >= 4) carries in the last cache tile
+    if (FOLD && g >= 4) {
+      int f = (NT - 1) * 8 + (g - 4);
+      if (f < a.q) {
+        int dd = f % (1 + a.D), km = f / (1 + a.D), mm = km % (a.M + 1), k = km / (a.M + 1);
+        zoffF = off_z + k * TM_STRIDE;
+        if (mm > 0) coffF = off_c + (mm - 1) * TM_STRIDE;
+        if (dd > 0) xoffF = off_x + (dd - 1) * TM_STRIDE;
+      }
+    }
     double R[MT][NT][2], S[NT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
@@ -318,6 +332,12 @@ __global__ void __launch_bounds__(TM_THREADS, BF_ST_BPS) stats_kernel_tma(const 
         }
         wv[nt] = w;
       }
+      if (FOLD && zoffF >= 0) {                       // rows 4..7 of the last cache tile (zero rows >= P) become W' rows
+        double2 w = *reinterpret_cast<const double2*>(base + zoffF);
+        if (coffF >= 0) { const double2 t = *reinterpret_cast<const double2*>(base + coffF); w.x *= t.x; w.y *= t.y; }
+        if (xoffF >= 0) { const double2 t = *reinterpret_cast<const double2*>(base + xoffF); w.x *= t.x; w.y *= t.y; }
+        av[MT - 1] = w;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);   // operands are in registers: the stage may be refilled
 #pragma unroll
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(TM_THREADS, BF_ST_BPS) stats_kernel_tma(const 
 #pragma unroll
         for (int n1 = 0; n1 < NT; n1++)
 #pragma unroll
-          for (int n2 = n1; n2 < NT; n2++) {
+          for (int n2 = n1; n2 < (FOLD ? NT - 1 : NT); n2++) {
             dmma884(S[n1][n2][0], S[n1][n2][1], wv[n1].x, wv[n2].x);
             dmma884(S[n1][n2][0], S[n1][n2][1], wv[n1].y, wv[n2].y);
           }
@@ -367,32 +387,88 @@ __global__ void __launch_bounds__(TM_THREADS, BF_ST_BPS) stats_kernel_tma(const 
 }
 
 // second stage: one warp per output element sums the block partials (lane-strided, then a shuffle
-// tree: a fixed order for a fixed grid, so the result is reproducible)
+// tree: a fixed order for a fixed grid, so the result is reproducible).
+//
+// Epilogue (a.ep): the sampler reads the reduced buffer on the host right behind this kernel, and on several GPUs sums
+// it over the shards first.  Both used to be kernels of their own (p2p_allreduce_kernel, copy_to_host_kernel); here the
+// last block to finish (ticket) does their work:
+//   * one GPU: it copies header and statistics into the mapped host copy (coalesced; element-wise 8-byte stores from
+//     the 48 reducing blocks were measured slower than the separate copy kernel: +4 us);
+//   * several GPUs: it stores the buffer into slot [rank] of EVERY rank's mailbox (remote stores over NVLink), publishes
+//     this rank's sequence number, waits for the others', sums the slots in rank order -- bit-identical on all ranks --
+//     and writes the totals to `stats` and to the host copy.
+// One launch instead of three between the contraction and the host's block draws.
 template <int MT, int NT>
-__global__ void __launch_bounds__(256) stats_final_kernel(const StatsArgs a, int gx) {
+__global__ void __launch_bounds__(256) stats_final_kernel(const StatsArgs a, int gx, int fold) {
   constexpr int TILES = MT * NT + NT * NT;
   const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int nR = a.P * a.q, nS = a.q * a.q;
-  if (e >= nR + nS) return;
-  int by, idx;
-  if (e < nR) {
-    int p = e % a.P, f = e / a.P;
-    int mtg = p >> 3;
-    by = mtg / MT;
-    idx = ((mtg % MT) * NT + (f >> 3)) * 64 + (p & 7) * 8 + (f & 7);
-  } else {
-    int s = e - nR;
-    int f1 = s % a.q, f2 = s / a.q;
-    if (f1 > f2) { int t = f1; f1 = f2; f2 = t; }     // only tiles n1 <= n2 are accumulated
-    by = 0;
-    idx = (MT * NT + (f1 >> 3) * NT + (f2 >> 3)) * 64 + (f1 & 7) * 8 + (f2 & 7);
+  if (e < nR + nS) {
+    int by, idx;
+    if (e < nR) {
+      int p = e % a.P, f = e / a.P;
+      int mtg = p >> 3;
+      by = mtg / MT;
+      idx = ((mtg % MT) * NT + (f >> 3)) * 64 + (p & 7) * 8 + (f & 7);
+    } else {
+      int s = e - nR;
+      int f1 = s % a.q, f2 = s / a.q;
+      if (f1 > f2) { int t = f1; f1 = f2; f2 = t; }     // only tiles n1 <= n2 are accumulated
+      by = 0;
+      idx = (MT * NT + (f1 >> 3) * NT + (f2 >> 3)) * 64 + (f1 & 7) * 8 + (f2 & 7);
+      // folded layout: W'W[f1][f2] with f2 in the remnant tile sits in row 4 + (f2 & 7) of cache tile (MT-1, f1 >> 3)
+      if (fold && (f2 >> 3) == NT - 1) idx = ((MT - 1) * NT + (f1 >> 3)) * 64 + (4 + (f2 & 7)) * 8 + (f1 & 7);
+    }
+    const double* base = a.partials + (size_t)by * gx * (TILES * 64) + idx;
+    double t = 0;
+    for (int b = lane; b < gx; b += 32) t += base[(size_t)b * (TILES * 64)];
+    t = warp_sum(t);
+    if (lane == 0) { if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t; }
   }
-  const double* base = a.partials + (size_t)by * gx * (TILES * 64) + idx;
-  double t = 0;
-  for (int b = lane; b < gx; b += 32) t += base[(size_t)b * (TILES * 64)];
-  t = warp_sum(t);
-  if (lane == 0) { if (e < nR) a.CtW[e] = t; else a.WtW[e - nR] = t; }
+  const StatsEpilogue& ep = a.ep;
+  const bool xchg = ep.world > 1;
+  if (!xchg && !ep.mirror) return;
+  // ---- epilogue: the last block to arrive sees every block's elements (fence + ticket)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ep.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ep.ticket = 0;
+  const int len = ep.hdr + nS + nR;          // [header (written by the Z / chi / SSR kernels before this one) | W'W | C~'W]
+  if (!xchg) {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) ep.mirror[i] = __ldcg(ep.stats + i);
+    return;
+  }
+  const int par = (int)(ep.seq & 1ull);
+  for (int r = 0; r < ep.world; r++) {       // (a) my partial sums into slot [par][rank] of every mailbox
+    double* dst = reinterpret_cast<double*>(ep.peers.box[r] + P2P_HDR) + ((size_t)par * ep.world + ep.rank) * ep.cap;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcg(ep.stats + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < ep.world) {              // (b) publish, (c) wait (bounded: a missing rank traps instead of hanging the device)
+    volatile unsigned long long* theirs = reinterpret_cast<volatile unsigned long long*>(ep.peers.box[threadIdx.x]) + ep.rank;
+    *theirs = ep.seq;
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(ep.peers.box[ep.rank]) + threadIdx.x;
+    unsigned long long spins = 0;
+    while (*mine < ep.seq) {
+      if (++spins > (1ull << 31)) __trap();
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // (d) sum in rank order
+  const double* src = reinterpret_cast<const double*>(ep.peers.box[ep.rank] + P2P_HDR) + (size_t)par * ep.world * ep.cap;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    double t = 0;
+    for (int r = 0; r < ep.world; r++) t += __ldcg(src + (size_t)r * ep.cap + i);
+    ep.stats[i] = t;
+    if (ep.mirror) ep.mirror[i] = t;
+  }
 }
 
 int stats_blocks(int sm_count) { return BF_ST_BPS * sm_count; }
@@ -436,8 +512,8 @@ static int launch_stats_x(const StatsArgs& a, int gy, cudaStream_t s) {
 }
 
 template <int MT, int NT>
-static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& used) {
-  used = false;
+static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& used, bool& folded) {
+  used = false; folded = false;
   static const bool disabled = std::getenv("BFMMM_STATS_NO_TMA") != nullptr;
   if (disabled || !a.tma || !a.tma->valid || a.tma->mt != MT || (a.ld % TM_FN) != 0) return 0;
   const size_t stage = (size_t)tm_align128(MT * 8 * TM_STRIDE) + tm_align128(a.K * TM_STRIDE) + tm_align128(a.M * TM_STRIDE) +
@@ -449,32 +525,37 @@ static int launch_stats_tma(const StatsArgs& a, int gy, cudaStream_t s, bool& us
   // The attribute is one value per (kernel, device) and the stage size depends on K, M, D, not only on <MT, NT>: it is
   // raised when an engine needs more than any before it (a set of the sizes seen would let a smaller engine lower it
   // under a larger one created earlier).  Several host threads may drive several engines: locked.
-  static std::map<int, size_t> granted;
+  static const bool no_fold = std::getenv("BFMMM_STATS_NO_FOLD") != nullptr;
+  const int pr = a.P & 7, qr = a.q & 7;
+  folded = !no_fold && gy == 1 && pr >= 1 && pr <= 4 && qr >= 1 && qr <= 4;
+  static std::map<std::pair<int, bool>, size_t> granted;
   static std::mutex granted_mu;
   {
     std::lock_guard<std::mutex> lock(granted_mu);
-    auto it = granted.find(dev);
+    auto it = granted.find({dev, folded});
     if (it == granted.end() || it->second < smem) {
-      cudaError_t e = cudaFuncSetAttribute(stats_kernel_tma<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = folded ? cudaFuncSetAttribute(stats_kernel_tma<MT, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(stats_kernel_tma<MT, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
-      granted[dev] = smem;
+      granted[{dev, folded}] = smem;
     }
   }
   dim3 grid(a.blocks, gy);
-  stats_kernel_tma<MT, NT><<<grid, TM_THREADS, smem, s>>>(a, *a.tma);
+  if (folded) stats_kernel_tma<MT, NT, true><<<grid, TM_THREADS, smem, s>>>(a, *a.tma);
+  else stats_kernel_tma<MT, NT, false><<<grid, TM_THREADS, smem, s>>>(a, *a.tma);
   used = true;
   return 0;
 }
 
 template <int MT, int NT>
 static int launch_stats_t(const StatsArgs& a, int gy, cudaStream_t s) {
-  bool used = false;
-  int rc = launch_stats_tma<MT, NT>(a, gy, s, used);
+  bool used = false, folded = false;
+  int rc = launch_stats_tma<MT, NT>(a, gy, s, used, folded);
   if (rc) return rc;
   if (!used) rc = a.D > 0 ? launch_stats_x<MT, NT, true>(a, gy, s) : launch_stats_x<MT, NT, false>(a, gy, s);
   if (rc) return rc;
   int tot = a.P * a.q + a.q * a.q;
-  stats_final_kernel<MT, NT><<<(tot + 7) / 8, 256, 0, s>>>(a, a.blocks);
+  stats_final_kernel<MT, NT><<<(tot + 7) / 8, 256, 0, s>>>(a, a.blocks, folded ? 1 : 0);
   g_launch_count += 2;
   return (int)cudaGetLastError();
 }

@@ -39,6 +39,9 @@ def _worker(rank, world, port, q, n_sweeps, hook="python"):
     if hook.endswith("_dev"):       # device-resident sweep: the exchanges are queued on the stream, no host read-back
         os.environ["BFMMM_DEVICE_GLOBALS"] = "1"
         hook = hook[:-4]
+    if hook.endswith("_sep"):       # peer-memory exchange as a kernel of its own (not fused into the statistics pass's epilogue)
+        os.environ["BFMMM_NO_FUSED_EXCHANGE"] = "1"
+        hook = hook[:-4]
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     bf, eng, smp, lo, hi = _setup(rank, world)
@@ -83,7 +86,7 @@ def _worker(rank, world, port, q, n_sweeps, hook="python"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("hook", ["python", "nccl", "p2p", "nccl_dev", "p2p_dev"])
+@pytest.mark.parametrize("hook", ["python", "nccl", "p2p", "p2p_sep", "nccl_dev", "p2p_dev"])
 def test_two_gpu_chain_follows_single_gpu_chain(hook):
     import torch
     if torch.cuda.device_count() < 2:

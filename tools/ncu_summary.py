@@ -76,7 +76,8 @@ def main():
         short = k.replace("void ", "").replace("bf::", "").split("<")[0]
         short = {"stats_kernel_tma": "stats_kernels", "ragged_stats_kernel": "ragged_stats_kernel"}.get(short, short)
         traffic[short] = traffic.get(short, 0.0) + (rd + wr) * scale
-        L.append(f"| `{k}` | {float(col(r, 'gpu__time_duration.sum')):.1f} | {rd * scale / 1e6:.1f} | {wr * scale / 1e6:.1f} | "
+        tu = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(rr[1][h.index("gpu__time_duration.sum")], 1.0)
+        L.append(f"| `{k}` | {float(col(r, 'gpu__time_duration.sum')) * tu:.1f} | {rd * scale / 1e6:.1f} | {wr * scale / 1e6:.1f} | "
                  f"{float(col(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
                  f"{float(col(r, 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')):.1f} | "
                  f"{float(col(r, 'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active')):.1f} | "
