@@ -239,8 +239,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Deterministic grid reduction of NV per-thread values: warp shuffle -> shared -> one partial row per
 // block -> the last block to finish (ticket) sums the rows in a fixed order and writes `out`.
+// returns true in the block that finished last (the one that wrote `out`)
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) {
+__device__ __forceinline__ bool grid_reduce_last(double (&v)[NV], const PassArgs& a) {
   __shared__ double s_part[PF_THREADS / 32][RED_MAX];
   __shared__ unsigned int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,7 +260,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) 
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
   // last block: NV values, each summed over gridDim.x rows by the whole block in a fixed pattern
   for (int j = 0; j < NV; j++) {
@@ -277,7 +278,10 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) 
     }
   }
   if (threadIdx.x == 0) *a.ticket = 0u;
+  return true;
 }
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], const PassArgs& a) { (void)grid_reduce_last<NV>(v, a); }
 
 // launchers implemented in the per-kernel translation units
 constexpr int BWMAX = 6;        // ragged grids: band width supported by the per-iteration kernels (degree <= 5)
@@ -287,7 +291,8 @@ int launch_ssr_ragged(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_z(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_z_propose(const PassArgs& a, int K, cudaStream_t s);                          // proposal half (any model)
 int launch_z_accept(const PassArgs& a, int K, int M, cudaStream_t s);                    // accept half, common basis
-int launch_moments(const PassArgs& a, int K, int M, double* mom, cudaStream_t s);          // moments_kernels.cu
+struct SigmaTail;
+int launch_moments(const PassArgs& a, int K, int M, double* mom, const SigmaTail* tail, cudaStream_t s);   // moments_kernels.cu
 int launch_chi_draw(const PassArgs& a, int K, int M, const double* mom, cudaStream_t s);
 int launch_chi(const PassArgs& a, int K, int M, cudaStream_t s);
 int launch_ssr(const PassArgs& a, int K, int M, cudaStream_t s);
@@ -310,6 +315,15 @@ struct StatsEpilogue {
   int hdr;                      // header slots [sum log Z (K) | accepts | ssr | ssr_after]
   unsigned* ticket;             // blocks-done counter (exchange only)
   P2PPeers peers; int rank, world, cap; unsigned long long seq;     // world <= 1: no exchange
+};
+// updateSigma's draw as the tail of its data pass: the block that finishes the SSR reduction last sums the SSR over the
+// shards (peer-memory mailboxes, world > 1), draws sigma^2 (UpdateSigma.h:47-53) and publishes (SSR, sigma^2, seq) in
+// mapped host memory -- what p2p_allreduce_kernel + sigma_draw_kernel did as two launches behind the pass.
+struct SigmaTail {
+  int on;
+  double shape, scale_ssr, beta0; uint64_t key, iteration; uint32_t purpose;
+  double* sigma_dev; double* host; double seq;
+  P2PPeers peers; int rank, world, cap; unsigned long long xseq;
 };
 struct StatsArgs {
   int n, ld, P, K, M, D, q;

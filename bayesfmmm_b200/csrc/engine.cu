@@ -798,22 +798,25 @@ int bfmmm_update_chi(bfmmm_engine* e, double beta, const double* eps, double* ss
   return 0;
 }
 
-int bfmmm_ssr_async(bfmmm_engine* e) {
-  if (!e) return fail("null engine");
-  CU(cudaSetDevice(e->device));
+static int ssr_launch(bfmmm_engine* e, const bf::SigmaTail* tail) {
   bf::PassArgs a;
   fill_pass(e, a, 1.0);
   a.out = e->stats + e->off_ssr(); a.n_out = 1;
   int rc;
   if (e->mom_enabled) {          // common basis, no covariates: the pass also leaves the chi step's moments
     if (!e->mom) CU(cudaMalloc(&e->mom, (size_t)e->ld * (e->M + 1) * 8));
-    rc = bf::launch_moments(a, e->K, e->M, e->mom, e->stream);
+    rc = bf::launch_moments(a, e->K, e->M, e->mom, tail, e->stream);
     e->mom_valid = (rc == 0);
   } else {
     rc = e->ragged ? bf::launch_ssr_ragged(a, e->K, e->M, e->stream) : bf::launch_ssr(a, e->K, e->M, e->stream);
   }
   if (rc) return fail("ssr kernel launch failed rc=" + std::to_string(rc));
   return 0;
+}
+int bfmmm_ssr_async(bfmmm_engine* e) {
+  if (!e) return fail("null engine");
+  CU(cudaSetDevice(e->device));
+  return ssr_launch(e, nullptr);
 }
 int bfmmm_ssr(bfmmm_engine* e, double* ssr, double* sum_half, double* n_points) {
   if (bfmmm_ssr_async(e)) return 1;
@@ -1120,6 +1123,30 @@ int bfmmm_debug_get_cache(bfmmm_engine* e, double* Ct, double* rss) {
 }  // extern "C"
 
 // ---- internal entry points of the device-resident sweep (engine_internal.h; not part of the C ABI)
+// updateSigma in one launch: the SSR pass with the sigma^2 draw (and, over several GPUs, the one-slot exchange of the SSR
+// through the peer-memory mailboxes) in its tail.  *done = 0 when the engine cannot do that (no moments pass for this
+// model, or an exchange is needed and the peer-memory exchange is not installed): nothing was launched then and the caller
+// runs bfmmm_ssr_async, its all-reduce hook and bfmmm_sigma_draw_async as before.
+int bfmmm_ssr_sigma_async(bfmmm_engine* e, int need_exchange, double a_shape, double scale_ssr, double beta0, uint64_t key,
+                          uint64_t iteration, uint32_t purpose, int* done) {
+  if (!e || !done) return fail("null argument");
+  *done = 0;
+  static const bool off = std::getenv("BFMMM_NO_SIGMA_TAIL") != nullptr;
+  if (off || !e->mom_enabled || (need_exchange && !e->xchg_on)) return 0;
+  CU(cudaSetDevice(e->device));
+  bf::SigmaTail t;
+  std::memset(&t, 0, sizeof(t));
+  t.on = 1; t.shape = a_shape; t.scale_ssr = scale_ssr; t.beta0 = beta0; t.key = key; t.iteration = iteration; t.purpose = purpose;
+  e->sig_seq += 1.0;
+  t.sigma_dev = e->sigma_dev; t.host = e->h_sig_dev; t.seq = e->sig_seq; t.world = 1;
+  if (need_exchange) {
+    t.peers = e->xchg_peers; t.rank = e->xchg_rank; t.world = e->xchg_world; t.cap = e->xchg_cap; t.xseq = ++*e->xchg_seq;
+  }
+  if (ssr_launch(e, &t)) return 1;
+  e->sigma_armed = true;
+  *done = 1;
+  return 0;
+}
 int64_t bfmmm_stats_len(bfmmm_engine* e) { return e ? e->stats_len : 0; }
 // 1 when the statistics pass queued last already summed the whole buffer over the shards in its epilogue
 int bfmmm_stats_exchanged(bfmmm_engine* e) { return e && e->stats_exchanged ? 1 : 0; }

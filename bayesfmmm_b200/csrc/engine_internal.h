@@ -32,3 +32,6 @@ double bfmmm_z_propose_us(bfmmm_engine* e);        // last proposal kernel timed
 int bfmmm_engine_set_exchange(bfmmm_engine* e, const bf::P2PPeers* peers, int rank, int world, int cap, unsigned long long* seq);
 int bfmmm_stats_exchanged(bfmmm_engine* e);        // the statistics pass queued last summed the buffer over the shards itself
 int64_t bfmmm_stats_len(bfmmm_engine* e);          // doubles in the statistics buffer
+// SSR pass + sigma^2 draw (+ one-slot exchange) in one launch; *done = 0: not available, nothing launched
+int bfmmm_ssr_sigma_async(bfmmm_engine* e, int need_exchange, double a_shape, double scale_ssr, double beta0, uint64_t key,
+                          uint64_t iteration, uint32_t purpose, int* done);

@@ -1460,18 +1460,24 @@ static int sampler_step_impl(bfmmm_sampler* s, int sweep, double beta) {
   }
   if (rc_blocks) return 1;
   if (push_globals(s)) return 1;
-  if (bfmmm_ssr_async(e)) return 1;                        // updateSigma's data pass, new globals
   // Fused path (no injected draws, no covariates): sigma^2 is drawn ON THE DEVICE right behind the SSR pass
   // -- same Philox stream (key, iteration, HP_SIGMA), same Marsaglia-Tsang sampler as the host draw -- and the
   // chi kernel is queued immediately behind it, so the device does not idle for a host round trip between
-  // the two passes.  The host takes (SSR, sigma^2) from mapped memory when it needs them.
+  // the two passes.  The host takes (SSR, sigma^2) from mapped memory when it needs them.  Where the engine can, the
+  // draw (and the exchange of the SSR slot over the shards) is the tail of the SSR pass itself: one launch, not three.
   const bool fused_sigma = do_chi && !s->D && !s->rng.use_tape && !std::getenv("BFMMM_NO_FUSED_SIGMA");
+  const double a_sh = tempered ? (beta * s->n_points_total) / 2 + s->h.alpha_0 : s->sum_half_total + s->h.alpha_0;
+  int tail_done = 0;
+  if (fused_sigma && bfmmm_ssr_sigma_async(e, s->allreduce ? 1 : 0, a_sh, tempered ? beta / 2 : 0.5, s->h.beta_0, s->rng.key,
+                                           s->rng.iteration, HP_SIGMA, &tail_done)) return 1;
+  if (!tail_done && bfmmm_ssr_async(e)) return 1;          // updateSigma's data pass, new globals
   if (fused_sigma) {
-    double* dev = nullptr; int64_t len = 0;
-    if (bfmmm_stats_buffer_dev(e, &dev, &len)) return 1;
-    if (s->allreduce && s->allreduce(s->allreduce_ctx, dev + s->K + 1, 1, bfmmm_stream(e))) return sfail("all-reduce hook failed");
-    const double a_sh = tempered ? (beta * s->n_points_total) / 2 + s->h.alpha_0 : s->sum_half_total + s->h.alpha_0;
-    if (bfmmm_sigma_draw_async(e, a_sh, tempered ? beta / 2 : 0.5, s->h.beta_0, s->rng.key, s->rng.iteration, HP_SIGMA)) return 1;
+    if (!tail_done) {
+      double* dev = nullptr; int64_t len = 0;
+      if (bfmmm_stats_buffer_dev(e, &dev, &len)) return 1;
+      if (s->allreduce && s->allreduce(s->allreduce_ctx, dev + s->K + 1, 1, bfmmm_stream(e))) return sfail("all-reduce hook failed");
+      if (bfmmm_sigma_draw_async(e, a_sh, tempered ? beta / 2 : 0.5, s->h.beta_0, s->rng.key, s->rng.iteration, HP_SIGMA)) return 1;
+    }
     if (bfmmm_update_chi_async(e, beta)) return 1;
   }
   if (do_z && !z_ahead) {                                  // updatePi_PM -> updateAlpha3

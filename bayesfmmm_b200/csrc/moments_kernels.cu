@@ -12,6 +12,7 @@
 // so they stay valid between the two calls (the engine invalidates them whenever Z, the globals or the data change and
 // falls back to chi_kernel's own pass).
 #include <cstdlib>
+#include <cstring>
 
 #include "pass_kernels.cuh"
 
@@ -20,8 +21,42 @@ namespace bf {
 #ifndef BF_MOM_MINB
 #define BF_MOM_MINB 4
 #endif
+// One thread, at the very end of the pass (out of line: the kernel's register budget is the streaming loop's).
+static __device__ __noinline__ void sigma_tail(double* ssr_slot, const SigmaTail& t) {
+  double ssr = *ssr_slot;
+  if (t.world > 1) {                       // one-slot exchange over the peers' mailboxes (protocol of p2p_hook.cu)
+    const int par = (int)(t.xseq & 1ull);
+    for (int r = 0; r < t.world; r++)
+      (reinterpret_cast<double*>(t.peers.box[r] + P2P_HDR) + ((size_t)par * t.world + t.rank) * t.cap)[0] = ssr;
+    __threadfence_system();
+    for (int r = 0; r < t.world; r++)
+      *(reinterpret_cast<volatile unsigned long long*>(t.peers.box[r]) + t.rank) = t.xseq;
+    for (int r = 0; r < t.world; r++) {
+      volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(t.peers.box[t.rank]) + r;
+      unsigned long long spins = 0;
+      while (*mine < t.xseq) {
+        if (++spins > (1ull << 31)) __trap();
+      }
+    }
+    __threadfence_system();
+    const double* src = reinterpret_cast<const double*>(t.peers.box[t.rank] + P2P_HDR) + (size_t)par * t.world * t.cap;
+    ssr = 0;
+    for (int r = 0; r < t.world; r++) ssr += __ldcg(src + (size_t)r * t.cap);     // rank order: same bits on every rank
+    *ssr_slot = ssr;
+  }
+  RngStream rs(t.key, 0xB200ull, t.iteration, t.purpose);      // the stream and sampler of sigma_draw_kernel / the host draw
+  const double b1 = t.scale_ssr * ssr + t.beta0;
+  const double r = (1 / b1) * rs.gamma(t.shape);
+  const double sig = 1 / r;
+  *t.sigma_dev = sig;
+  volatile double* host = t.host;
+  host[0] = ssr; host[1] = sig;
+  __threadfence_system();
+  host[2] = t.seq;
+}
+
 template <int K, int M, int V>
-__global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const PassArgs a, double* __restrict__ mom) {
+__global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const PassArgs a, double* __restrict__ mom, const SigmaTail tail) {
   extern __shared__ double g[];
   stage_globals(a, g);
   constexpr int NKK = K * (K + 1) / 2, NMN = M * (M + 1) / 2;
@@ -104,7 +139,8 @@ __global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const 
     for (int m = 0; m < M; m++) stv<V>(mom + (size_t)m * a.ld + i0, rr[m]);
     stv<V>(mom + (size_t)M * a.ld + i0, base);
   }
-  grid_reduce<1>(red, a);
+  const bool last = grid_reduce_last<1>(red, a);
+  if (tail.on && last && threadIdx.x == 0) sigma_tail(a.out, tail);
 }
 
 template <int K, int M, int V>
@@ -194,11 +230,13 @@ __global__ void __launch_bounds__(PF_THREADS, 8) chi_draw_kernel(const PassArgs 
 
 constexpr int MV = 2, DV = 1;
 #define BF_CASE_moments(KK, MM) \
-  case KK * 16 + MM: return cov ? -3 : launch_pass<MV>(moments_kernel<KK, MM, MV>, a, s, 0, mom);
+  case KK * 16 + MM: return cov ? -3 : launch_pass<MV>(moments_kernel<KK, MM, MV>, a, s, 0, mom, tl);
 #define BF_CASE_chidraw(KK, MM) \
   case KK * 16 + MM: return cov ? -3 : launch_pass<DV>(chi_draw_kernel<KK, MM, DV>, a, s, 0, (const double*)mom);
 
-int launch_moments(const PassArgs& a, int K, int M, double* mom, cudaStream_t s) {
+int launch_moments(const PassArgs& a, int K, int M, double* mom, const SigmaTail* tail, cudaStream_t s) {
+  SigmaTail tl;
+  if (tail) tl = *tail; else { std::memset(&tl, 0, sizeof(tl)); }
   BF_DISPATCH(moments)
 }
 int launch_chi_draw(const PassArgs& a, int K, int M, const double* mom, cudaStream_t s) {
