@@ -22,7 +22,8 @@ namespace bf {
 #define BF_MOM_MINB 4
 #endif
 // One thread, at the very end of the pass (out of line: the kernel's register budget is the streaming loop's).
-static __device__ __noinline__ void sigma_tail(double* ssr_slot, const SigmaTail& t) {
+static __device__ __noinline__ void sigma_tail(double* ssr_slot, const SigmaTail* tp) {
+  const SigmaTail& t = *tp;
   double ssr = *ssr_slot;
   if (t.world > 1) {                       // one-slot exchange over the peers' mailboxes (protocol of p2p_hook.cu)
     const int par = (int)(t.xseq & 1ull);
@@ -56,7 +57,8 @@ static __device__ __noinline__ void sigma_tail(double* ssr_slot, const SigmaTail
 }
 
 template <int K, int M, int V>
-__global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const PassArgs a, double* __restrict__ mom, const SigmaTail tail) {
+__global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const PassArgs a, double* __restrict__ mom,
+                                                                          const __grid_constant__ SigmaTail tail) {
   extern __shared__ double g[];
   stage_globals(a, g);
   constexpr int NKK = K * (K + 1) / 2, NMN = M * (M + 1) / 2;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(PF_THREADS, BF_MOM_MINB) moments_kernel(const 
     stv<V>(mom + (size_t)M * a.ld + i0, base);
   }
   const bool last = grid_reduce_last<1>(red, a);
-  if (tail.on && last && threadIdx.x == 0) sigma_tail(a.out, tail);
+  if (tail.on && last && threadIdx.x == 0) sigma_tail(a.out, &tail);
 }
 
 template <int K, int M, int V>
