@@ -63,6 +63,24 @@ def source_hash() -> str:
     return h.hexdigest()
 
 
+# translation units without device code of the sweep: the driver loop, the all-reduce hooks, file I/O, host linear algebra
+_HOST_ONLY = {"host_sampler.cu", "p2p_hook.cu", "nccl_hook.cu", "host_linalg.cpp", "arma_io.cu", "basis_host.cu"}
+
+
+def kernel_source_hash() -> str:
+    """md5 over the device-code sources (csrc/ minus the host-only translation units): the key of the committed ncu
+    traffic evidence -- a kernel's DRAM bytes do not depend on the host loop around it."""
+    import hashlib
+    h = hashlib.md5()
+    d = os.path.join(_HERE, "csrc")
+    for f in sorted(os.listdir(d)):
+        if f in _HOST_ONLY:
+            continue
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
 def build_library(jobs: int = 8, extra: str = "") -> str:
     """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_HERE, "csrc"), f"-j{jobs}", "-s"]

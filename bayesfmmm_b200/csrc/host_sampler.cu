@@ -925,6 +925,9 @@ int bfmmm_sampler_create_detached(const int32_t* dims, const bfmmm_hyper* h, int
 }
 void bfmmm_sampler_destroy(bfmmm_sampler* s) {
   if (s) dev_free(s);
+  // an exchange fused into the engine's passes points into the hook's context (mailboxes, sequence counter), which the
+  // caller frees after the sampler: the engine must not outlive it with that wiring
+  if (s && s->e) bfmmm_engine_set_exchange(s->e, nullptr, 0, 1, 0, nullptr);
   delete s;
 }
 // 1 when the sampler's sweeps run device-resident (globals_kernels.cu), 0 when the host draws the globals
@@ -947,6 +950,8 @@ int bfmmm_sampler_set_counts(bfmmm_sampler* s, double sum_half_total, double n_p
 }
 int bfmmm_sampler_set_allreduce(bfmmm_sampler* s, bfmmm_allreduce_fn fn, void* ctx) {
   if (!s) return sfail("null sampler");
+  // a new hook replaces the fused peer-memory exchange of an earlier one (bfmmm_sampler_enable_p2p re-installs its own)
+  if (s->e && bfmmm_engine_set_exchange(s->e, nullptr, 0, 1, 0, nullptr)) return 1;
   s->allreduce = fn; s->allreduce_ctx = ctx;
   return 0;
 }

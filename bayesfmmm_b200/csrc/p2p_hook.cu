@@ -123,11 +123,13 @@ int bfmmm_sampler_enable_p2p(bfmmm_sampler* s, void* ctx, const char* handles) {
     c->opened.push_back(p);
     c->peers.box[r] = (unsigned char*)p;
   }
-  // The whole-buffer exchange behind the statistics pass runs inside that pass's final reduction (stats_kernels.cu:
-  // same mailboxes, same sequence counter); the hook below remains for the one-slot exchanges (SSR, log-likelihood).
+  if (bfmmm_sampler_set_allreduce(s, p2p_allreduce, c)) return 1;
+  // The whole-buffer exchange behind the statistics pass runs inside that pass's final reduction and the SSR slot's
+  // inside the SSR pass (stats_kernels.cu, moments_kernels.cu: same mailboxes, same sequence counter); the hook above
+  // remains for the other one-slot exchanges (log-likelihood flush, models without the fused passes).
   if (bfmmm_engine* e = bfmmm_sampler_engine(s))
     if (bfmmm_engine_set_exchange(e, &c->peers, c->rank, c->world, c->cap, &c->seq)) return 1;
-  return bfmmm_sampler_set_allreduce(s, p2p_allreduce, c);
+  return 0;
 }
 
 void bfmmm_p2p_destroy(void* ctx) {

@@ -585,14 +585,15 @@ def run_ours(a):
              for k, v in kern.items()}
     dom = max(kinfo, key=lambda k: kinfo[k]["ms"])
     # dram bytes of the same kernel from the committed `ncu --set full` capture (profiles/r02_traffic.json), used only
-    # when that capture was taken on a build of exactly these sources (md5 over csrc/ and include/) and this shard size
+    # when that capture was taken on a build of exactly these device-code sources (md5 over csrc/ minus the host-only
+    # translation units, bayesfmmm_b200/_lib.py:kernel_source_hash) and this shard size
     traffic, traffic_src = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tr.get(a.workload, {})
-        if ent.get("n_per_gpu") == n and ent.get("source_md5") == bf._lib.source_hash():
+        if ent.get("n_per_gpu") == n and ent.get("source_md5") == bf._lib.kernel_source_hash():
             traffic = ent["kernels"].get(dom)
-            traffic_src = "profiles/r02_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same sources: md5 over csrc/ and include/)"
+            traffic_src = "profiles/r02_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, same device-code sources: md5 over csrc/ minus the host-only translation units)"
         elif ent:
             traffic_src = "profiles/r02_traffic.json was captured on another build or shard size: not reported"
     except Exception:

@@ -77,7 +77,10 @@ void bfmmm_nccl_destroy(void* comm);
  * every rank calls bfmmm_p2p_create (its mailbox + 64-byte CUDA IPC handle), the handles are all-gathered
  * by the caller, then bfmmm_sampler_enable_p2p maps the peers and installs the hook.  Results are summed in
  * rank order on every rank (bit-identical).  A barrier over all ranks must separate enable from the first
- * sweep and the last sweep from bfmmm_p2p_destroy. */
+ * sweep and the last sweep from bfmmm_p2p_destroy.  With this hook the engine runs the whole-buffer exchange inside
+ * the statistics pass's final reduction and the SSR slot's inside the SSR pass (no kernels of their own), so while it is installed bfmmm_suffstats* on this engine is a
+ * collective every rank must enter; that wiring
+ * ends with bfmmm_sampler_destroy or a later bfmmm_sampler_set_allreduce: destroy the sampler BEFORE bfmmm_p2p_destroy. */
 int bfmmm_p2p_create(int rank, int world, int64_t cap, void** ctx_out, char* handle_out /* 64 bytes */);
 int bfmmm_sampler_enable_p2p(bfmmm_sampler* s, void* ctx, const char* handles /* world x 64 bytes */);
 void bfmmm_p2p_destroy(void* ctx);

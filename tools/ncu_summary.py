@@ -4,8 +4,9 @@
 
 The capture is either the report itself or its `ncu -i report --page raw --csv` export (a report of the full library
 embeds its 60 MB of cubins and does not fit the 64 MiB that travel back from the GPU box, so the export is made there).
-<tag>_traffic.json is keyed by bench.py's workload and kernel names and carries the md5 of the sources (csrc/, include/) the
-captured library was built from: bench.py reports `roofline.traffic` from it only when its own sources hash to the same.
+<tag>_traffic.json is keyed by bench.py's workload and kernel names and carries the md5 of the device-code sources (csrc/ minus the
+host-only translation units, `_lib.kernel_source_hash`) the captured library was built from: bench.py reports `roofline.traffic`
+from it only when its own sources hash to the same.
 """
 import hashlib
 import collections
@@ -90,7 +91,7 @@ def main():
     path = os.path.join(out_dir, f"{tag}_traffic.json")
     doc = json.load(open(path)) if os.path.exists(path) else {}
     doc["unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, first launch of each kernel)"
-    doc[workload] = {"n_per_gpu": n_per_gpu, "source_md5": _lib.source_hash(), "kernels": traffic}
+    doc[workload] = {"n_per_gpu": n_per_gpu, "source_md5": _lib.kernel_source_hash(), "kernels": traffic}
     json.dump(doc, open(path, "w"), indent=1)
     print("\n".join(L[-8:]))
 
