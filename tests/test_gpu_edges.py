@@ -66,7 +66,7 @@ def test_largest_and_smallest_supported_shapes(K, M, P, D):
     eps = np.asfortranarray(rng.normal(size=(50, M)))
     ssr_after = eng.update_chi(1.0, eps=eps)
     chi_o = orc.update_chi(d, st, eps)
-    assert rel(eng.get_state(Z=False)[1], chi_o) < 1e-9
+    assert rel(eng.get_state(Z=False)[1], chi_o) < TOL      # measured 2e-15 .. 3e-15 on these shapes (B200)
     eng.set_state(s["Z"], s["chi"])
     gam = np.asfortranarray(rng.gamma(20000.0 * s["Z"])); u = rng.uniform(size=50)
     Zo, acc, _ = orc.update_z(d, st, s["pi"], 1.0, 20000.0, gam, u)
@@ -195,6 +195,8 @@ def test_rank_deficient_basis(kind):
     eps = np.asfortranarray(rng.normal(size=(n, M)))
     ssr_after = eng.update_chi(1.0, eps=eps)
     chi_o = orc.update_chi(d, st, eps)
+    # rank-deficient Gram: the cache is whitened by eigenvectors with a relative eigenvalue cut-off, the oracle
+    # works per observed point; 1e-9 is the bar here (not re-measured this round)
     assert rel(eng.get_state(Z=False)[1], chi_o) < 1e-9
     eng.set_state(Z, chi)
     gam = np.asfortranarray(rng.gamma(20000.0 * Z)); u = rng.uniform(size=n)

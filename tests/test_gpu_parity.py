@@ -228,7 +228,8 @@ def test_ragged_sweep_matches_oracle_updates(name):
     WtW, BtYW, Hb = eng.suffstats_ragged(4)
     smp.set_hband(Hb)
     smp.tape(dr["z_nu"].ravel(order="F")); smp.host_update("nu", WtW, BtYW, 1.0)
-    assert rel(smp.get()["nu"], orc.update_nu(d, st, dr["tau"], orc.pmat_rw1(d.P), dr["z_nu"])) < 1e-8
+    # measured 3e-15 .. 4e-14 (B200; the C4 shape's 666 pair bands are the largest)
+    assert rel(smp.get()["nu"], orc.update_nu(d, st, dr["tau"], orc.pmat_rw1(d.P), dr["z_nu"])) < TOL
     smp.close(); eng.close()
 
 
